@@ -1,0 +1,119 @@
+/*
+ * qbm_b200.h -- C ABI of libqbm_b200.so, the B200 (sm_100a) implementation of the
+ * sampling-and-training hot path of Mark-Seebode/QBM-Image-Classification.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless marked "host";
+ *     the library allocates nothing and performs no host<->device copies or synchronisation
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is
+ *     enqueued on it and the call returns immediately
+ *   - return value: 0 on success, a negative QBM_E* code otherwise; the message is available
+ *     from qbm_last_error() (thread-local); nothing is thrown across the ABI
+ *   - citations "ref:" are into /root/reference (the interface each entry point replaces)
+ */
+#ifndef QBM_B200_H
+#define QBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define QBM_API __attribute__((visibility("default")))
+#else
+#define QBM_API
+#endif
+
+#define QBM_OK            0
+#define QBM_EINVAL       -1   /* bad argument (shape, alignment, null pointer) */
+#define QBM_EUNSUPPORTED -2   /* size outside what the kernels are built for */
+#define QBM_ECUDA        -3   /* CUDA runtime error (message holds cudaGetErrorString) */
+#define QBM_EWORKSPACE   -4   /* caller workspace too small (see *_workspace_bytes) */
+
+#define QBM_SA_MAX_N   2048   /* largest QUBO the SA kernel is instantiated for */
+
+int         qbm_version(void);              /* ABI version, currently 1 */
+const char *qbm_last_error(void);           /* host string, thread-local */
+/* sm_count / cc_major / cc_minor of the current device (host out-pointers, nullable). */
+int         qbm_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * K0  dense QUBO -> spin model.
+ * ref: dimod.BQM(Q, "BINARY") + change_vartype(SPIN) as called from src/qubo/sampler.py:7-8,31
+ *      and src/model/faster_dqbm.py:577,619.
+ *   Q        [batch, n, n] float64 row-major (any triangle layout; b_ij = Q_ij + Q_ji)
+ *   J_out    [batch, n, n] float32 symmetric couplings J_ij = b_ij/4, zero diagonal
+ *   h_out    [batch, n]    float32 h_i = Q_ii/2 + sum_j b_ij/4   (accumulated in float64)
+ *   offset   [batch]       float64 sum_i Q_ii/2 + sum_{i<j} b_ij/4            (nullable)
+ *   range    [batch, 2]    float64 {min non-zero |bias|, max_i (|h_i| + sum_j |J_ij|)}: the two
+ *                          numbers neal's legacy _default_ising_beta_range reduces to (A.4);
+ *                          {0, 0} when every bias is zero                      (nullable)
+ */
+int qbm_qubo_to_ising(const double *Q, int n, long long batch, float *J_out, float *h_out,
+                      double *offset, double *range, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  simulated-annealing sampler (one warp per read/chain).
+ * ref: neal.SimulatedAnnealingSampler.sample -> cpu_sa.cpp, reached through
+ *      src/qubo/sampler.py:31-33 (LocalSASampler.sample_Q) and
+ *      src/model/faster_dqbm.py:299-313 (Disc_QBM.sample_sa) -- SURVEY.md Appendix A.5.
+ *   J, h      spin model of `batch_q` problems: J [batch_q, n, ldj] float32 (symmetric, zero
+ *             diagonal, ldj >= n), h [batch_q, n] float32
+ *   beta      [batch_q or 1, num_betas] float32 inverse temperatures; beta_stride = elements
+ *             between consecutive problems' schedules (0 = one schedule shared by all)
+ *   sweeps_per_beta  sweeps at each beta (neal: max(1, num_sweeps // 1000))
+ *   num_reads chains per problem; chain g = chain_offset + q*num_reads + r keys the Philox
+ *             stream, so results do not depend on how reads are sharded over launches/GPUs
+ *   init_states  nullable [batch_q, num_reads, n] int8 0/1; NULL = Philox initial states
+ *   states_out   [batch_q, num_reads, n] int8 0/1, read order (what dimod calls record.sample)
+ *   counters     nullable uint64[2]: += accepted flips, += proposals
+ *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned
+ *   flags        bit 0: disable the per-window CTA rendezvous (debug / A-B measurements)
+ */
+size_t qbm_sa_workspace_bytes(int n, long long batch_q);
+int qbm_sa_sample(const float *J, const float *h, int n, int ldj, long long batch_q,
+                  const float *beta, long long beta_stride, int num_betas, int sweeps_per_beta,
+                  long long num_reads, uint64_t seed, uint64_t chain_offset,
+                  const int8_t *init_states, int8_t *states_out, unsigned long long *counters,
+                  void *workspace, size_t workspace_bytes, unsigned flags, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2  batched QUBO energies  E[q, r] = x^T Q_q x  in float64.
+ * ref: neal get_state_energy + dimod offset = the BINARY energy in SampleSet.record.energy
+ *      (SURVEY.md A.2/A.6).
+ *   Q [batch_q, n, n] float64, states [batch_q, R, n] int8 0/1, energy_out [batch_q, R] float64
+ */
+int qbm_qubo_energy(const double *Q, int n, long long batch_q, const int8_t *states, long long R,
+                    double *energy_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3  phase statistics: first and second moments of a sample set.
+ * ref: the np.average / (block^T @ block) / n_reads reductions in
+ *      src/train/train.py:135-253 (get_average_configuration_single) and
+ *      src/model/discriminative_qbm.py:696-760 (get_average_configuration).
+ *   states [batch_q, R, n] int8 0/1
+ *   mean_out   [batch_q, n]    float32  <s_i>
+ *   second_out [batch_q, n, n] float32  <s_i s_j> (full symmetric matrix), nullable
+ *   workspace  scratch of at least qbm_phase_stats_workspace_bytes(batch_q, R, n) bytes
+ * Counts are accumulated as exact integers (bit-plane popcounts) and divided by R once.
+ */
+size_t qbm_phase_stats_workspace_bytes(long long batch_q, long long R, int n);
+int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n, float *mean_out,
+                    float *second_out, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that
+ * tests can compare them bit-for-bit with the oracle's independent C restatement.
+ *   qbm_test_philox: ctr [count,4] u32, key [count,2] u32 -> out [count,4] u32
+ *   qbm_test_exp:    x [count] f32 -> out [count] f32 (exp_spec of DESIGN.md section 3)
+ */
+int qbm_test_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out, long long count, void *stream);
+int qbm_test_exp(const float *x, float *out, long long count, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QBM_B200_H */

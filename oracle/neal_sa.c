@@ -1,0 +1,146 @@
+/*
+ * oracle/neal_sa.c -- TEST INFRASTRUCTURE ONLY (never imported by the product path).
+ *
+ * CPU restatement (float64, one serial xorshift128+ stream, reads processed strictly in
+ * order) of the Metropolis loop the reference reaches through
+ *   src/qubo/sampler.py:31-33            LocalSASampler.sample_Q -> neal .sample(...)
+ *   src/model/faster_dqbm.py:299-313     Disc_QBM.sample_sa / parallel_sa_sample
+ *   src/model/discriminative_qbm.py:314-329
+ * i.e. dwave-neal==0.5.9 (requirements.txt:3), neal/src/cpu_sa.cpp.  That dependency is NOT
+ * vendored in /root/reference and is not installable here, so this file restates its
+ * published algorithm as pinned in SURVEY.md Appendix A.5/A.6:
+ *   - dE[v] = -2 s_v (h_v + sum_nb J s_nb) kept per variable, updated on every accepted flip
+ *   - fixed sweep order v = 0..n-1; skip when dE >= 44.36142/beta; accept when dE <= 0;
+ *     otherwise accept iff exp(-dE*beta) * (2^64-1) > xorshift128+()
+ *   - rng state {seed ? seed : 2^64-1, 0}, continuing across reads
+ *   - energy = sum h_i s_i + sum_{couplers} J_ij s_i s_j
+ * PARITY STATUS: sample-level parity is UNPINNED (the reference holds no golden sample sets
+ * and neal itself is absent); what pins this file is (i) exact identities tested in
+ * tests/test_oracle_sa.py (energy bookkeeping, brute-force ground states, detailed balance)
+ * and (ii) the reference's recorded accuracies reproduced through it (tests/golden/).
+ *
+ * Build: make -C oracle   (gcc -O2 -shared -fPIC)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct { uint64_t s0, s1; } xs128p_t;
+
+static inline uint64_t xs128p_next(xs128p_t *g)
+{
+    uint64_t x = g->s0;
+    const uint64_t y = g->s1;
+    g->s0 = y;
+    x ^= x << 23;
+    g->s1 = x ^ y ^ (x >> 17) ^ (y >> 26);
+    return g->s1 + y;
+}
+
+/* adjacency in CSR form built from the coupler list (both directions) */
+typedef struct {
+    int n;
+    int *start;     /* n+1 */
+    int *nbr;       /* 2*nnz */
+    double *w;      /* 2*nnz */
+} adj_t;
+
+static int adj_build(adj_t *a, int n, int nnz, const int *irow, const int *icol, const double *jv)
+{
+    a->n = n;
+    a->start = (int *)calloc((size_t)n + 1, sizeof(int));
+    a->nbr = (int *)malloc(sizeof(int) * (size_t)(2 * nnz + 1));
+    a->w = (double *)malloc(sizeof(double) * (size_t)(2 * nnz + 1));
+    if (!a->start || !a->nbr || !a->w) return -1;
+    for (int k = 0; k < nnz; ++k) {
+        if (irow[k] < 0 || irow[k] >= n || icol[k] < 0 || icol[k] >= n || irow[k] == icol[k]) return -2;
+        a->start[irow[k] + 1]++;
+        a->start[icol[k] + 1]++;
+    }
+    for (int i = 0; i < n; ++i) a->start[i + 1] += a->start[i];
+    int *fill = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+    if (!fill) return -1;
+    memcpy(fill, a->start, sizeof(int) * (size_t)n);
+    for (int k = 0; k < nnz; ++k) {
+        int u = irow[k], v = icol[k];
+        a->nbr[fill[u]] = v; a->w[fill[u]++] = jv[k];
+        a->nbr[fill[v]] = u; a->w[fill[v]++] = jv[k];
+    }
+    free(fill);
+    return 0;
+}
+
+static void adj_free(adj_t *a) { free(a->start); free(a->nbr); free(a->w); }
+
+static double flip_energy(const adj_t *a, const double *h, const signed char *s, int v)
+{
+    double e = h[v];
+    for (int k = a->start[v]; k < a->start[v + 1]; ++k) e += (double)s[a->nbr[k]] * a->w[k];
+    return -2.0 * (double)s[v] * e;
+}
+
+static double state_energy(const adj_t *a, const double *h, const signed char *s)
+{
+    double e = 0.0;
+    for (int v = 0; v < a->n; ++v) e += h[v] * (double)s[v];
+    for (int v = 0; v < a->n; ++v)
+        for (int k = a->start[v]; k < a->start[v + 1]; ++k)
+            if (a->nbr[k] > v) e += (double)s[v] * a->w[k] * (double)s[a->nbr[k]];
+    return e;
+}
+
+/*
+ * states: [num_reads, n] of +/-1, initial states on entry, final states on exit.
+ * counters (nullable) [3]: accepted flips, threshold skips, random draws.
+ * Returns 0, or <0 on bad input / allocation failure.
+ */
+int oracle_neal_sa(int n, const double *h, int nnz, const int *irow, const int *icol, const double *jv,
+                   int num_reads, signed char *states, int num_betas, const double *betas,
+                   int sweeps_per_beta, uint64_t seed, double *energies, uint64_t *counters)
+{
+    adj_t a;
+    int rc = adj_build(&a, n, nnz, irow, icol, jv);
+    if (rc) return rc;
+    double *de = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    if (!de) { adj_free(&a); return -1; }
+    xs128p_t g = { seed ? seed : UINT64_MAX, 0 };
+    uint64_t n_acc = 0, n_skip = 0, n_draw = 0;
+
+    for (int r = 0; r < num_reads; ++r) {
+        signed char *s = states + (size_t)r * (size_t)n;
+        for (int v = 0; v < n; ++v) de[v] = flip_energy(&a, h, s, v);
+        for (int b = 0; b < num_betas; ++b) {
+            const double beta = betas[b];
+            for (int sw = 0; sw < sweeps_per_beta; ++sw) {
+                const double threshold = 44.36142 / beta;
+                for (int v = 0; v < n; ++v) {
+                    if (de[v] >= threshold) { ++n_skip; continue; }
+                    int flip = 0;
+                    if (de[v] <= 0.0) {
+                        flip = 1;
+                    } else {
+                        const uint64_t rnd = xs128p_next(&g);
+                        ++n_draw;
+                        if (exp(-de[v] * beta) * (double)UINT64_MAX > (double)rnd) flip = 1;
+                    }
+                    if (flip) {
+                        const signed char mult = (signed char)(4 * s[v]);
+                        for (int k = a.start[v]; k < a.start[v + 1]; ++k) {
+                            const int nb = a.nbr[k];
+                            de[nb] += (double)mult * a.w[k] * (double)s[nb];
+                        }
+                        s[v] = (signed char)-s[v];
+                        de[v] = -de[v];
+                        ++n_acc;
+                    }
+                }
+            }
+        }
+        if (energies) energies[r] = state_energy(&a, h, s);
+    }
+    if (counters) { counters[0] = n_acc; counters[1] = n_skip; counters[2] = n_draw; }
+    free(de);
+    adj_free(&a);
+    return 0;
+}

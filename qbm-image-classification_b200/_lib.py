@@ -1,0 +1,75 @@
+"""ctypes binding of libqbm_b200.so (the C ABI declared in include/qbm_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libqbm_b200.so")
+
+QBM_OK = 0
+QBM_EINVAL = -1
+QBM_EUNSUPPORTED = -2
+QBM_ECUDA = -3
+QBM_EWORKSPACE = -4
+QBM_SA_MAX_N = 2048
+
+_c_i = ctypes.c_int
+_c_ll = ctypes.c_longlong
+_c_u64 = ctypes.c_uint64
+_c_sz = ctypes.c_size_t
+_c_p = ctypes.c_void_p
+_c_u = ctypes.c_uint
+
+# name -> (restype, argtypes); must list every symbol include/qbm_b200.h declares
+SIGNATURES = {
+    "qbm_version": (_c_i, []),
+    "qbm_last_error": (ctypes.c_char_p, []),
+    "qbm_device_info": (_c_i, [_c_p, _c_p, _c_p]),
+    "qbm_qubo_to_ising": (_c_i, [_c_p, _c_i, _c_ll, _c_p, _c_p, _c_p, _c_p, _c_p]),
+    "qbm_sa_workspace_bytes": (_c_sz, [_c_i, _c_ll]),
+    "qbm_sa_sample": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_ll, _c_p, _c_ll, _c_i, _c_i, _c_ll, _c_u64, _c_u64,
+                             _c_p, _c_p, _c_p, _c_p, _c_sz, _c_u, _c_p]),
+    "qbm_qubo_energy": (_c_i, [_c_p, _c_i, _c_ll, _c_p, _c_ll, _c_p, _c_p]),
+    "qbm_phase_stats_workspace_bytes": (_c_sz, [_c_ll, _c_ll, _c_i]),
+    "qbm_phase_stats": (_c_i, [_c_p, _c_ll, _c_ll, _c_i, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "qbm_test_philox": (_c_i, [_c_p, _c_p, _c_p, _c_ll, _c_p]),
+    "qbm_test_exp": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
+}
+
+_lib = None
+
+
+class QbmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libqbm_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python __graft_entry__.py` (or "
+                "`python qbm-image-classification_b200/build.py`) to compile the CUDA extension; "
+                "there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != QBM_OK:
+        msg = load().qbm_last_error().decode("utf-8", "replace")
+        if rc in (QBM_EINVAL, QBM_EUNSUPPORTED, QBM_EWORKSPACE):
+            raise ValueError(f"libqbm_b200 error {rc}: {msg}")
+        raise QbmError(rc, msg)

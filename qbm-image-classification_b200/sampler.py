@@ -1,0 +1,238 @@
+"""Sampler boundary B1: a drop-in for ``src/qubo/sampler.py`` whose native
+loop is the sm_100a kernel instead of dwave-neal's ``cpu_sa.cpp``.
+
+* :class:`B200SASampler` mirrors ``LocalSASampler`` (src/qubo/sampler.py:19-33): same constructor
+  (``num_sweeps``, ``seed``), same ``sample_Q(Q, num_reads) -> float32 [num_reads, n]`` of 0/1 in read
+  order, same linear-only shortcut (:13-17, :28-29).  It can be assigned to ``model.sampler``
+  (src/model/cdqbm_state.py:55) unchanged.
+* :func:`sa_sample` is the batched device-level call under it (torch tensors in, torch tensors out,
+  no host synchronisation) used by the training loops and the benchmark.
+
+PyTorch is used only as the owner of device buffers and streams; all arithmetic of the path runs in
+libqbm_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, ising
+
+
+def _stream_ptr(device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("qbm_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+@dataclass
+class SAResult:
+    states: torch.Tensor            # int8 [batch_q, num_reads, n] of 0/1, read order
+    accepted: torch.Tensor | None   # uint64-as-int64 [2]: accepted flips, proposals (when counted)
+
+
+def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_beta: int, num_reads: int,
+              seed: int, chain_offset: int = 0, init_states: torch.Tensor | None = None,
+              count: bool = False, flags: int = 0, workspace: torch.Tensor | None = None,
+              out: torch.Tensor | None = None) -> SAResult:
+    """Anneal ``num_reads`` chains for each of ``batch_q`` spin models on the current CUDA stream.
+
+    ``J`` float32 [batch_q, n, n] (symmetric, zero diagonal), ``h`` float32 [batch_q, n],
+    ``betas`` float32 [batch_q, num_betas] or [1, num_betas] / [num_betas] (shared schedule).
+    """
+    L = _lib.load()
+    if J.dim() == 2:
+        J = J[None]
+    if h.dim() == 1:
+        h = h[None]
+    if betas.dim() == 1:
+        betas = betas[None]
+    if not (J.is_cuda and h.is_cuda and betas.is_cuda):
+        raise ValueError("sa_sample: J, h and betas must be CUDA tensors")
+    if J.dtype != torch.float32 or h.dtype != torch.float32 or betas.dtype != torch.float32:
+        raise ValueError("sa_sample: J, h and betas must be float32")
+    J = J.contiguous(); h = h.contiguous(); betas = betas.contiguous()
+    bq, n, n2 = J.shape
+    if n != n2 or h.shape != (bq, n):
+        raise ValueError(f"sa_sample: inconsistent shapes J={tuple(J.shape)} h={tuple(h.shape)}")
+    if betas.shape[0] not in (1, bq):
+        raise ValueError("sa_sample: betas must have 1 or batch_q rows")
+    num_betas = betas.shape[1]
+    beta_stride = 0 if betas.shape[0] == 1 else num_betas
+    dev = J.device
+    need = L.qbm_sa_workspace_bytes(n, bq)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty((need + 15) // 16 * 4, dtype=torch.float32, device=dev)
+    if out is None:
+        out = torch.empty((bq, num_reads, n), dtype=torch.int8, device=dev)
+    elif out.shape != (bq, num_reads, n) or out.dtype != torch.int8 or not out.is_contiguous():
+        raise ValueError("sa_sample: `out` must be a contiguous int8 [batch_q, num_reads, n] tensor")
+    init_ptr = None
+    if init_states is not None:
+        if init_states.shape != (bq, num_reads, n) or init_states.dtype != torch.int8:
+            raise ValueError("sa_sample: init_states must be int8 [batch_q, num_reads, n]")
+        init_states = init_states.contiguous()
+        init_ptr = init_states.data_ptr()
+    counters = torch.zeros(2, dtype=torch.int64, device=dev) if count else None
+    with torch.cuda.device(dev):
+        rc = L.qbm_sa_sample(J.data_ptr(), h.data_ptr(), n, n, bq, betas.data_ptr(), beta_stride, num_betas,
+                             int(sweeps_per_beta), int(num_reads), ctypes.c_uint64(int(seed) & (2 ** 64 - 1)),
+                             ctypes.c_uint64(int(chain_offset)), init_ptr, out.data_ptr(),
+                             counters.data_ptr() if counters is not None else None,
+                             workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                             int(flags), _stream_ptr(dev))
+    _lib.check(rc)
+    return SAResult(states=out, accepted=counters)
+
+
+def qubo_energies(Q: torch.Tensor, states: torch.Tensor) -> torch.Tensor:
+    """float64 [batch_q, R] energies x^T Q x of int8 0/1 ``states`` [batch_q, R, n] (K2)."""
+    L = _lib.load()
+    if Q.dim() == 2:
+        Q = Q[None]
+    if states.dim() == 2:
+        states = states[None]
+    if Q.dtype != torch.float64 or states.dtype != torch.int8 or not Q.is_cuda or not states.is_cuda:
+        raise ValueError("qubo_energies: Q must be CUDA float64 and states CUDA int8")
+    Q = Q.contiguous(); states = states.contiguous()
+    bq, n, _ = Q.shape
+    if states.shape[0] != bq or states.shape[2] != n:
+        raise ValueError(f"qubo_energies: inconsistent shapes Q={tuple(Q.shape)} states={tuple(states.shape)}")
+    R = states.shape[1]
+    out = torch.empty((bq, R), dtype=torch.float64, device=Q.device)
+    with torch.cuda.device(Q.device):
+        rc = L.qbm_qubo_energy(Q.data_ptr(), n, bq, states.data_ptr(), R, out.data_ptr(), _stream_ptr(Q.device))
+    _lib.check(rc)
+    return out
+
+
+def phase_stats(states: torch.Tensor, second: bool = True):
+    """(mean float32 [batch_q, n], second float32 [batch_q, n, n] or None) of int8 0/1 states (K3)."""
+    L = _lib.load()
+    if states.dim() == 2:
+        states = states[None]
+    if states.dtype != torch.int8 or not states.is_cuda:
+        raise ValueError("phase_stats: states must be a CUDA int8 tensor")
+    states = states.contiguous()
+    bq, R, n = states.shape
+    dev = states.device
+    mean = torch.empty((bq, n), dtype=torch.float32, device=dev)
+    sec = torch.empty((bq, n, n), dtype=torch.float32, device=dev) if second else None
+    need = L.qbm_phase_stats_workspace_bytes(bq, R, n)
+    ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.qbm_phase_stats(states.data_ptr(), bq, R, n, mean.data_ptr(), sec.data_ptr() if second else None,
+                               ws.data_ptr(), ws.numel() * 4, _stream_ptr(dev))
+    _lib.check(rc)
+    return mean, sec
+
+
+def qubo_to_ising_device(Q: torch.Tensor):
+    """K0 on the device: (J f32 [B,n,n], h f32 [B,n], offset f64 [B], range f64 [B,2])."""
+    L = _lib.load()
+    if Q.dim() == 2:
+        Q = Q[None]
+    if Q.dtype != torch.float64 or not Q.is_cuda:
+        raise ValueError("qubo_to_ising_device: Q must be a CUDA float64 tensor")
+    Q = Q.contiguous()
+    B, n, _ = Q.shape
+    dev = Q.device
+    J = torch.empty((B, n, n), dtype=torch.float32, device=dev)
+    h = torch.empty((B, n), dtype=torch.float32, device=dev)
+    off = torch.empty(B, dtype=torch.float64, device=dev)
+    rng = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.qbm_qubo_to_ising(Q.data_ptr(), n, B, J.data_ptr(), h.data_ptr(), off.data_ptr(), rng.data_ptr(),
+                                 _stream_ptr(dev))
+    _lib.check(rc)
+    return J, h, off, rng
+
+
+# ------------------------------------------------------------------------------------------------
+# host-level call: numpy QUBOs in, numpy samples out (what the reference's call sites exchange)
+# ------------------------------------------------------------------------------------------------
+def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, seed=None, beta_range=None,
+                      beta_schedule_type: str = "geometric", initial_states_generator: str = "numpy",
+                      device=None, return_energy: bool = True, chain_offset: int = 0):
+    """Sample a batch of dense QUBOs ``[B, n, n]`` (float64, host).  Host logic (spin conversion, beta
+    range, schedule, initial states) follows neal/dimod in float64 (:mod:`ising`); the annealing, the
+    energies and nothing else run on the GPU.
+
+    Returns ``(samples int8 [B, R, n] numpy, energies float64 [B, R] numpy or None, info dict)``.
+    """
+    dev = _require_cuda(device)
+    Q = np.asarray(Q, dtype=np.float64)
+    single = Q.ndim == 2
+    if single:
+        Q = Q[None]
+    B, n, _ = Q.shape
+    seed = ising.check_seed(seed)
+    if seed is None:
+        seed = int(np.random.randint(2 ** 31))
+    h, J, offset = ising.qubo_to_ising(Q)
+    if beta_range is None:
+        br = ising.default_beta_range(h, J)
+    else:
+        br = np.broadcast_to(np.asarray(beta_range, dtype=np.float64), (B, 2))
+    betas, spb = ising.beta_schedule(br, num_sweeps, beta_schedule_type)
+    Jd = torch.from_numpy(J.astype(np.float32)).to(dev, non_blocking=True)
+    hd = torch.from_numpy(h.astype(np.float32)).to(dev, non_blocking=True)
+    bd = torch.from_numpy(betas.astype(np.float32)).to(dev, non_blocking=True)
+    init = None
+    if initial_states_generator == "numpy":
+        # the reference passes the same seed on every call, so every problem of the batch starts
+        # from the same RandomState(seed) draw
+        st0 = ising.initial_states_numpy(seed, num_reads, n)
+        init = torch.from_numpy(np.broadcast_to(st0, (B, num_reads, n)).copy()).to(dev)
+    elif initial_states_generator != "philox":
+        raise ValueError("initial_states_generator must be 'numpy' or 'philox'")
+    res = sa_sample(Jd, hd, bd, spb, num_reads, seed, chain_offset=chain_offset, init_states=init)
+    energies = None
+    if return_energy:
+        Qd = torch.from_numpy(Q).to(dev)
+        energies = qubo_energies(Qd, res.states).cpu().numpy()
+    samples = res.states.cpu().numpy()
+    info = {"beta_range": br.tolist() if not single else br[0].tolist(), "beta_schedule_type": beta_schedule_type,
+            "num_betas": int(betas.shape[1]), "sweeps_per_beta": spb, "offset": offset}
+    return samples, energies, info
+
+
+class B200SASampler:
+    """Drop-in for ``LocalSASampler`` (src/qubo/sampler.py:19-33)."""
+
+    def __init__(self, num_sweeps: int = 1000, seed: int | None = None, initial_states_generator: str = "numpy",
+                 device=None):
+        self.num_sweeps = int(num_sweeps)
+        self.seed = seed
+        self.initial_states_generator = initial_states_generator
+        self.device = device
+
+    def sample_Q(self, Q: np.ndarray, num_reads: int) -> np.ndarray:
+        Q = np.asarray(Q, dtype=np.float64)
+        if Q.ndim != 2 or Q.shape[0] != Q.shape[1]:
+            raise ValueError(f"Q must be a square matrix, got shape {Q.shape}")
+        if bool(ising.is_linear_only(Q)[0]):
+            return _solve_linear_only(Q, int(num_reads), self.seed)
+        samples, _, _ = sample_qubo_batch(Q, int(num_reads), self.num_sweeps, self.seed,
+                                          initial_states_generator=self.initial_states_generator,
+                                          device=self.device, return_energy=False)
+        return samples[0].astype(np.float32)
+
+
+def _solve_linear_only(Q: np.ndarray, num_reads: int, seed) -> np.ndarray:
+    """src/qubo/sampler.py:13-17: the argmin solution replicated ``num_reads`` times (host-side branch;
+    not a thermal sample -- SURVEY.md Appendix B Q7)."""
+    rng = np.random.default_rng(seed)
+    n = Q.shape[0]
+    sol = np.zeros(n, dtype=np.float32)
+    for v in range(n):
+        hv = Q[v, v]
+        sol[v] = 1 if hv < 0 else (0 if hv > 0 else int(rng.integers(0, 2)))
+    return np.tile(sol, (num_reads, 1)).astype(np.float32)

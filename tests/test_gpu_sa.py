@@ -1,0 +1,148 @@
+"""GPU parity tests of the sampler path (K0-K3) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_qubo
+
+pytestmark = pytest.mark.gpu
+
+
+def _prep(qbm, Q, num_sweeps):
+    h, J, off = qbm.ising.qubo_to_ising(Q)
+    br = qbm.ising.default_beta_range(h, J)
+    betas, spb = qbm.ising.beta_schedule(br, num_sweeps)
+    return h[0].astype(np.float32), J[0].astype(np.float32), betas[0].astype(np.float32), spb
+
+
+def test_device_philox_matches_oracle(qbm, oracle, cuda):
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, size=(4096, 4), dtype=np.uint64).astype(np.uint32)
+    key = rng.integers(0, 2 ** 32, size=(4096, 2), dtype=np.uint64).astype(np.uint32)
+    ctr[0] = 0; key[0] = 0
+    ctr[1] = 0xFFFFFFFF; key[1] = 0xFFFFFFFF
+    c = torch.from_numpy(ctr.view(np.int32)).to(cuda)
+    k = torch.from_numpy(key.view(np.int32)).to(cuda)
+    o = torch.empty_like(c)
+    L = qbm._lib.load()
+    qbm._lib.check(L.qbm_test_philox(c.data_ptr(), k.data_ptr(), o.data_ptr(), 4096, None))
+    torch.cuda.synchronize()
+    got = o.cpu().numpy().view(np.uint32)
+    # Random123 known-answer vectors
+    assert got[0].tolist() == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert got[1].tolist() == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    for i in range(0, 4096, 37):
+        assert got[i].tolist() == oracle.philox4x32_10(ctr[i], key[i]).tolist()
+
+
+def test_device_exp_spec_bit_exact(qbm, oracle, cuda):
+    rng = np.random.default_rng(2)
+    x = -rng.uniform(0, 44.4, 20000).astype(np.float32)
+    x[:4] = [0.0, -1e-30, -44.36, -1.0]
+    xd = torch.from_numpy(x).to(cuda)
+    od = torch.empty_like(xd)
+    L = qbm._lib.load()
+    qbm._lib.check(L.qbm_test_exp(xd.data_ptr(), od.data_ptr(), x.size, None))
+    got = od.cpu().numpy()
+    ref = np.array([oracle.exp_spec(float(v)) for v in x], dtype=np.float32)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.max(np.abs(got - np.exp(x.astype(np.float64))) / np.exp(x.astype(np.float64))) < 2e-7
+
+
+@pytest.mark.parametrize("n,reads,sweeps,density", [
+    (1, 5, 50, 1.0), (7, 16, 200, 1.0), (24, 33, 1000, 1.0), (32, 9, 300, 1.0), (33, 9, 300, 1.0),
+    (34, 40, 1000, 1.0), (64, 8, 300, 1.0), (65, 8, 300, 0.5), (100, 8, 400, 1.0), (128, 8, 300, 1.0),
+    (129, 8, 300, 1.0), (193, 12, 1000, 0.89), (256, 6, 200, 1.0), (300, 6, 200, 1.0), (522, 6, 1000, 1.0),
+    (700, 4, 100, 1.0), (1000, 4, 100, 1.0), (1200, 3, 100, 1.0), (1500, 3, 100, 1.0), (2048, 3, 1000, 1.0),
+])
+def test_trajectory_bit_exact_vs_replay(qbm, oracle, cuda, n, reads, sweeps, density):
+    """The kernel's final states equal the sequential CPU replay of the reference's Metropolis rule fed
+    the same Philox stream (north_star correctness criterion 2) -- every bit of every read."""
+    Q = random_qubo(n, seed=19 + n, density=density)
+    h, J, betas, spb = _prep(qbm, Q, sweeps)
+    seed, off = 0x1234ABCD5678EF01 ^ n, 7 * n
+    res = qbm.sa_sample(torch.from_numpy(J).to(cuda), torch.from_numpy(h).to(cuda), torch.from_numpy(betas).to(cuda),
+                        spb, reads, seed, chain_offset=off, count=True)
+    got = res.states.cpu().numpy()[0]
+    ref, counters = oracle.replay_sample(J, h, betas, spb, seed, off, reads)
+    assert np.array_equal(got, ref)
+    acc = res.accepted.cpu().numpy().astype(np.uint64)
+    assert int(acc[0]) == int(counters[0])
+    assert int(acc[1]) == reads * n * len(betas) * spb
+
+
+def test_trajectory_with_host_initial_states_and_batch(qbm, oracle, cuda):
+    """batch_q problems with individual schedules + host (numpy RandomState) initial states."""
+    B, n, reads, sweeps = 5, 41, 20, 300
+    Qs = np.stack([random_qubo(n, seed=100 + b, scale=1.0 + b) for b in range(B)])
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
+    init = np.stack([qbm.ising.initial_states_numpy(44 + b, reads, n) for b in range(B)])
+    J32, h32, b32 = J.astype(np.float32), h.astype(np.float32), betas.astype(np.float32)
+    res = qbm.sa_sample(torch.from_numpy(J32).to(cuda), torch.from_numpy(h32).to(cuda), torch.from_numpy(b32).to(cuda),
+                        spb, reads, 77, init_states=torch.from_numpy(init).to(cuda))
+    got = res.states.cpu().numpy()
+    for b in range(B):
+        ref, _ = oracle.replay_sample(J32[b], h32[b], b32[b], spb, 77, b * reads, reads, init01=init[b])
+        assert np.array_equal(got[b], ref), f"problem {b}"
+
+
+def test_sharding_invariance(qbm, cuda):
+    """Reads keyed by their global index: two half-launches equal one full launch (multi-GPU sharding)."""
+    n, reads = 150, 64
+    Q = random_qubo(n, seed=5)
+    h, J, betas, spb = _prep(qbm, Q, 200)
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J, h, betas))
+    full = qbm.sa_sample(Jd, hd, bd, spb, reads, 9).states
+    a = qbm.sa_sample(Jd, hd, bd, spb, reads // 2, 9, chain_offset=0).states
+    b = qbm.sa_sample(Jd, hd, bd, spb, reads // 2, 9, chain_offset=reads // 2).states
+    assert torch.equal(full[0], torch.cat([a[0], b[0]], dim=0))
+    # the CTA rendezvous is a performance hint only: results are identical without it
+    nosync = qbm.sa_sample(Jd, hd, bd, spb, reads, 9, flags=1).states
+    assert torch.equal(full, nosync)
+
+
+@pytest.mark.parametrize("n,R,B", [(1, 3, 1), (24, 100, 3), (34, 77, 2), (193, 130, 1), (522, 65, 1), (2048, 70, 1)])
+def test_energies_vs_oracle(qbm, oracle, cuda, n, R, B):
+    rng = np.random.default_rng(n)
+    Qs = np.stack([random_qubo(n, seed=n + b) for b in range(B)])
+    if n == 24:
+        Qs[1] = rng.uniform(-1, 1, (n, n))            # a full (non-triangular) matrix is legal input
+    X = (rng.random((B, R, n)) < 0.5).astype(np.int8)
+    got = qbm.qubo_energies(torch.from_numpy(Qs).to(cuda), torch.from_numpy(X).to(cuda)).cpu().numpy()
+    for b in range(B):
+        ref = oracle.qubo_energies(Qs[b], X[b])
+        assert np.allclose(got[b], ref, rtol=1e-12, atol=1e-9 * n)   # criterion: <= 1e-6 relative
+
+
+@pytest.mark.parametrize("n,R,B", [(1, 1, 1), (24, 100, 4), (34, 31, 2), (193, 1000, 2), (522, 100, 1), (300, 4100, 1)])
+def test_phase_stats_exact(qbm, cuda, n, R, B):
+    rng = np.random.default_rng(n + R)
+    X = (rng.random((B, R, n)) < rng.random((B, 1, n))).astype(np.int8)
+    mean, sec = qbm.phase_stats(torch.from_numpy(X).to(cuda))
+    Xf = X.astype(np.float64)
+    ref_mean = Xf.mean(axis=1)
+    ref_sec = np.einsum("bri,brj->bij", Xf, Xf) / R
+    assert np.array_equal(mean.cpu().numpy(), ref_mean.astype(np.float32))
+    assert np.array_equal(sec.cpu().numpy(), ref_sec.astype(np.float32))
+    mean2, none = qbm.phase_stats(torch.from_numpy(X).to(cuda), second=False)
+    assert none is None and torch.equal(mean, mean2)
+
+
+def test_qubo_to_ising_device_matches_host(qbm, cuda):
+    for n, B in [(1, 1), (24, 7), (193, 2), (522, 1)]:
+        Qs = np.stack([random_qubo(n, seed=3 * n + b, density=0.7) for b in range(B)])
+        Qs[0, 0, 0] = 0.0
+        h, J, off = qbm.ising.qubo_to_ising(Qs)
+        br = qbm.ising.default_beta_range(h, J)
+        Jd, hd, od, rd = qbm.qubo_to_ising_device(torch.from_numpy(Qs).to(cuda))
+        assert np.array_equal(Jd.cpu().numpy(), J.astype(np.float32))
+        assert np.allclose(hd.cpu().numpy(), h.astype(np.float32), rtol=3e-7, atol=1e-7)
+        assert np.allclose(od.cpu().numpy(), off, rtol=1e-13, atol=1e-12)
+        r = rd.cpu().numpy()
+        if n > 1:
+            assert np.allclose(np.log(2) / r[:, 1], br[:, 0], rtol=1e-13)
+            assert np.allclose(np.log(100) / r[:, 0], br[:, 1], rtol=1e-13)
+    Z = torch.zeros((1, 3, 3), dtype=torch.float64, device=cuda)
+    _, _, _, rz = qbm.qubo_to_ising_device(Z)
+    assert rz.cpu().numpy().tolist() == [[0.0, 0.0]]
