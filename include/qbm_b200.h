@@ -95,14 +95,15 @@ int qbm_qubo_energy(const double *Q, int n, long long batch_q, const int8_t *sta
  *      src/train/train.py:135-253 (get_average_configuration_single) and
  *      src/model/discriminative_qbm.py:696-760 (get_average_configuration).
  *   states [batch_q, R, n] int8 0/1
- *   mean_out   [batch_q, n]    float32  <s_i>
- *   second_out [batch_q, n, n] float32  <s_i s_j> (full symmetric matrix), nullable
+ *   mean_out   [batch_q, n]    float64  <s_i>
+ *   second_out [batch_q, n, n] float64  <s_i s_j> (full symmetric matrix), nullable
  *   workspace  scratch of at least qbm_phase_stats_workspace_bytes(batch_q, R, n) bytes
- * Counts are accumulated as exact integers (bit-plane popcounts) and divided by R once.
+ * Counts are accumulated as exact integers (bit-plane popcounts) and divided by R once in float64,
+ * which is bit-identical to numpy's float64 mean of 0/1 products.
  */
 size_t qbm_phase_stats_workspace_bytes(long long batch_q, long long R, int n);
-int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n, float *mean_out,
-                    float *second_out, void *workspace, size_t workspace_bytes, void *stream);
+int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n, double *mean_out,
+                    double *second_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that

@@ -33,7 +33,7 @@ constexpr int TS = 32;    // variables per tile side
 constexpr int WCH = 32;   // words staged per chunk
 
 __global__ void __launch_bounds__(256) stats_pair_kernel(const uint32_t *__restrict__ bits, long long R, int n, int Rw,
-                                                         float *__restrict__ mean_out, float *__restrict__ second_out)
+                                                         double *__restrict__ mean_out, double *__restrict__ second_out)
 {
     const int bi = blockIdx.x, bj = blockIdx.y;
     if (bj < bi) return;                          // symmetric: upper tiles only, mirrored on store
@@ -65,16 +65,15 @@ __global__ void __launch_bounds__(256) stats_pair_kernel(const uint32_t *__restr
         }
         __syncthreads();
     }
-    const double invR = 1.0 / (double)R;
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
         for (int b = 0; b < 2; ++b) {
             const int gi = bi * TS + 2 * ti + a, gj = bj * TS + 2 * tj + b;
             if (gi < n && gj < n) {
-                const float val = (float)((double)cnt[a][b] * invR);
+                const double val = (double)cnt[a][b] / (double)R;   // the exact rational, rounded once
                 if (second_out != nullptr) {
-                    float *S2 = second_out + q * (size_t)n * (size_t)n;
+                    double *S2 = second_out + q * (size_t)n * (size_t)n;
                     S2[(size_t)gi * n + gj] = val;
                     S2[(size_t)gj * n + gi] = val;
                 }
@@ -92,8 +91,8 @@ extern "C" QBM_API size_t qbm_phase_stats_workspace_bytes(long long batch_q, lon
     return (size_t)batch_q * (size_t)n * Rw * sizeof(uint32_t);
 }
 
-extern "C" QBM_API int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n, float *mean_out,
-                               float *second_out, void *workspace, size_t workspace_bytes, void *stream)
+extern "C" QBM_API int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n, double *mean_out,
+                               double *second_out, void *workspace, size_t workspace_bytes, void *stream)
 {
     QBM_CHECK_ARG(states && mean_out && workspace, "qbm_phase_stats: null pointer argument");
     QBM_CHECK_ARG(batch_q >= 1 && R >= 1 && n >= 1, "qbm_phase_stats: batch_q, R and n must be >= 1");

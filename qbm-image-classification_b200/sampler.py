@@ -114,7 +114,7 @@ def qubo_energies(Q: torch.Tensor, states: torch.Tensor) -> torch.Tensor:
 
 
 def phase_stats(states: torch.Tensor, second: bool = True):
-    """(mean float32 [batch_q, n], second float32 [batch_q, n, n] or None) of int8 0/1 states (K3)."""
+    """(mean float64 [batch_q, n], second float64 [batch_q, n, n] or None) of int8 0/1 states (K3)."""
     L = _lib.load()
     if states.dim() == 2:
         states = states[None]
@@ -123,8 +123,8 @@ def phase_stats(states: torch.Tensor, second: bool = True):
     states = states.contiguous()
     bq, R, n = states.shape
     dev = states.device
-    mean = torch.empty((bq, n), dtype=torch.float32, device=dev)
-    sec = torch.empty((bq, n, n), dtype=torch.float32, device=dev) if second else None
+    mean = torch.empty((bq, n), dtype=torch.float64, device=dev)
+    sec = torch.empty((bq, n, n), dtype=torch.float64, device=dev) if second else None
     need = L.qbm_phase_stats_workspace_bytes(bq, R, n)
     ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):

@@ -123,8 +123,8 @@ def test_phase_stats_exact(qbm, cuda, n, R, B):
     Xf = X.astype(np.float64)
     ref_mean = Xf.mean(axis=1)
     ref_sec = np.einsum("bri,brj->bij", Xf, Xf) / R
-    assert np.array_equal(mean.cpu().numpy(), ref_mean.astype(np.float32))
-    assert np.array_equal(sec.cpu().numpy(), ref_sec.astype(np.float32))
+    assert np.array_equal(mean.cpu().numpy(), ref_mean)          # bit-identical to numpy's float64 means
+    assert np.array_equal(sec.cpu().numpy(), ref_sec)
     mean2, none = qbm.phase_stats(torch.from_numpy(X).to(cuda), second=False)
     assert none is None and torch.equal(mean, mean2)
 

@@ -1,0 +1,121 @@
+"""CPU: the numpy oracle of the model-side hot path against the golden fixtures produced by the
+reference's own Python (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import model_oracle as M
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name), allow_pickle=False)
+
+
+def params(g, prefix):
+    return {k: g[f"{prefix}_{k}"] for k in ("W_vh", "W_vo", "W_oo", "b_h", "b_o", "W_hh")}
+
+
+def test_disc_qbm_loop_onehot_matches_reference():
+    g = load("disc_qbm_loop_onehot.npz")
+    p0 = params(g, "w0")
+    X, Y = g["X"], g["Y"]
+    for i in range(4):
+        assert np.array_equal(M.disc_qubo(p0, X[i], Y[i]), g["Qc"][i])
+        assert np.array_equal(M.disc_qubo(p0, X[i]), g["Qu"][i])
+        c = M.disc_stats_loop(g["Sc"][i], X[i], Y[i], 10, 16, 24)
+        u = M.disc_stats_loop(g["Su"][i], X[i], None, 10, 16, 24)
+        for nm, a, b in zip(["b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh"], c, u):
+            assert np.allclose(a, g[f"stat_c_{nm}_{i}"], rtol=0, atol=1e-15), nm
+            assert np.allclose(b, g[f"stat_u_{nm}_{i}"], rtol=0, atol=1e-15), nm
+    p1 = M.disc_train_step(p0, X, Y, g["Sc"], g["Su"], float(g["lr"]), "loop")
+    for k, v in p1.items():
+        assert np.allclose(v, g[f"w1_{k}"], rtol=0, atol=1e-14), k
+
+
+def test_disc_qbm_faster_binary_matches_reference():
+    g = load("disc_qbm_faster_binary.npz")
+    p0 = params(g, "w0")
+    X, Y = g["X"], g["Y"]
+    for i in range(5):
+        assert np.array_equal(M.disc_qubo(p0, X[i], Y[i]), g["Qc"][i])
+        assert np.array_equal(M.disc_qubo(p0, X[i]), g["Qu"][i])
+    c = M.disc_stats_faster_batch(g["Sc"], X, [[y] for y in Y], 1, 20, 6)
+    u = M.disc_stats_faster_batch(g["Su"], X, None, 1, 20, 6)
+    for nm, a, b in zip(["b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh"], c, u):
+        assert np.allclose(a, g[f"stat_c_{nm}"], rtol=0, atol=1e-14), nm
+        assert np.allclose(b, g[f"stat_u_{nm}"], rtol=0, atol=1e-14), nm
+    assert abs(M.disc_nll(g["Su"], Y) - float(g["nll"])) < 1e-6
+    p1 = M.disc_train_step(p0, X, Y, g["Sc"], g["Su"], float(g["lr"]), "faster")
+    for k, v in p1.items():
+        assert np.allclose(v, g[f"w1_{k}"], rtol=0, atol=1e-14), k
+    assert np.array_equal(p1["W_hh"], p0["W_hh"])          # Appendix B Q2: W_hh is never trained there
+
+
+@pytest.mark.parametrize("name,one_hot", [("convdeep_binary.npz", False), ("convdeep_onehot.npz", True)])
+def test_convdeep_matches_reference(name, one_hot):
+    g = load(name)
+    p0 = dict(kernel=g["w0_kernel"], W_seq=[g["w0_W_seq0"]], W_intra=[g["w0_W_intra0"]], W_hy=g["w0_W_hy"],
+              W_oo=g["w0_W_oo"], b_conv=g["w0_b_conv"], b_seq=g["w0_b_seq"], b_out=g["w0_b_out"])
+    n_lab = p0["b_out"].shape[0]
+    X, Y = g["X"], g["Y"]
+    for i in range(3):
+        flat, pooled, patches = M.convdeep_context(X[i], p0["kernel"], 1, 2)
+        lab = np.eye(n_lab)[Y[i]] if one_hot else np.array([float(Y[i])])
+        assert np.allclose(M.convdeep_qubo(p0, flat, pooled, lab), g["Qc"][i], rtol=0, atol=1e-15)
+        assert np.allclose(M.convdeep_qubo(p0, flat, pooled, None), g["Qu"][i], rtol=0, atol=1e-15)
+        P = len(pooled)
+        assert np.allclose(M.convdeep_probs(g["Su"][i], P + 12, one_hot), g["probs"][i])
+        for tag, S, yy in (("c", g["Sc"][i], lab), ("u", g["Su"][i], None)):
+            r = M.convdeep_stats(S.astype(np.float32), X[i], yy, P, [12], n_lab, patches)
+            for nm, a in zip(["b_conv", "b_seq", "b_out", "kernel", "W_intra", "W_seq", "W_hy", "W_oo"], r):
+                a = a[0] if isinstance(a, list) else a
+                assert np.allclose(a, g[f"stat_{tag}_{nm}_{i}"], rtol=1e-6, atol=1e-7), (tag, nm)
+    new, loss = M.convdeep_train_step(p0, X, Y, g["Sc"].astype(np.float32), g["Su"].astype(np.float32),
+                                      float(g["lr"]), 1, 2, one_hot)
+    assert abs(loss - float(g["loss"])) < 1e-6
+    for k, ref in [("kernel", "kernel"), ("W_hy", "W_hy"), ("W_oo", "W_oo"), ("b_conv", "b_conv"), ("b_seq", "b_seq"),
+                   ("b_out", "b_out")]:
+        assert np.allclose(new[k], g[f"w1_{ref}"], rtol=1e-6, atol=1e-7), k
+    assert np.allclose(new["W_seq"][0], g["w1_W_seq0"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(new["W_intra"][0], g["w1_W_intra0"], rtol=1e-6, atol=1e-7)
+
+
+def test_rbm_matches_reference():
+    g = load("rbm_discriminative.npz")
+    W, U, bv, bh, bc = g["W0"], g["U0"], g["bv0"], g["bh0"], g["bc0"]
+    x, y = g["x"], g["y"]
+    onehot = np.eye(10, dtype=np.float32)[y[0]]
+    assert np.allclose(M.rbm_sample_hidden(W, U, bh, x[0], onehot), g["ph0"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(M.rbm_sample_visible(W, bv, g["hbin"]), g["pv0"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(M.rbm_sample_class(U, bc, g["hbin"]), g["pc0"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(M.rbm_class_given_x(W, U, bh, bc, x[0]), g["pyx0"], rtol=1e-4, atol=1e-6)
+    for s in range(2):
+        new, probs, pred, err = M.rbm_discriminative_step(W, U, bv, bh, bc, x[s], y[s], float(g["lr"]))
+        assert np.allclose(probs, g[f"probs{s}"], rtol=1e-4, atol=1e-6)
+        assert np.array_equal(pred, g[f"pred{s}"])
+        assert abs(err - float(g[f"err{s}"])) < 1e-5
+        W, U, bv, bh, bc = new["W"], new["U"], new["b_v"], new["b_h"], new["b_c"]
+        assert np.allclose(W, g[f"W{s + 1}"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(U, g[f"U{s + 1}"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(bh, g[f"bh{s + 1}"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(bc, g[f"bc{s + 1}"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(bv, g[f"bv{s + 1}"], rtol=1e-6, atol=1e-7)
+
+
+def test_recorded_accuracy_by_exact_enumeration():
+    """The reference's own recorded test accuracy (out/paper_data/.../e20_*_testacc_auc.pkl) is reproduced
+    exactly by the ground state of the unclamped QUBO the oracle builds from the saved weights."""
+    from sklearn.metrics import roc_auc_score
+    g = load("pneumonia_h10_recorded_accuracy.npz")
+    labels = g["labels"].astype(int)
+    for k in range(3):
+        off, diag = g[f"off_{k}"], g[f"diag_{k}"]
+        n = diag.shape[1]
+        X = ((np.arange(2 ** n)[:, None] >> np.arange(n)) & 1).astype(np.float64)
+        quad = np.einsum("ri,ij,rj->r", X, off, X)
+        pred = np.array([int(X[np.argmin(X @ d + quad), 0]) for d in diag])
+        assert abs(np.mean(pred == labels) - float(g[f"acc_{k}"])) < 1e-12
+        assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12
