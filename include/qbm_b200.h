@@ -72,6 +72,8 @@ int qbm_qubo_to_ising(const double *Q, int n, long long batch, float *J_out, flo
  *   counters     nullable uint64[2]: += accepted flips, += proposals
  *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned
  *   flags        bit 0: disable the per-window CTA rendezvous (debug / A-B measurements)
+ *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
+ *                       stream, as the reference's fixed per-call seed does)
  */
 size_t qbm_sa_workspace_bytes(int n, long long batch_q);
 int qbm_sa_sample(const float *J, const float *h, int n, int ldj, long long batch_q,

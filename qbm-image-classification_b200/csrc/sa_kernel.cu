@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     const float *__restrict__ J = p.Jp + (size_t)q * (size_t)n * (size_t)ld;
     const float *__restrict__ hq = p.hp + (size_t)q * (size_t)ld;
     const float *__restrict__ betas = p.beta + q * p.beta_stride;
-    const unsigned long long chain = p.chain_offset + (unsigned long long)cl;
+    // flag bit 1: key the stream by the read index only, so every problem of the batch sees the same
+    // random stream -- what the reference does by passing the same seed to every call (Appendix B Q6)
+    const unsigned long long chain = p.chain_offset + (unsigned long long)((p.flags & 2u) ? (cl - q * p.num_reads) : cl);
     const uint32_t c_lo = (uint32_t)chain, c_hi = (uint32_t)(chain >> 32);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     const bool rendezvous = (p.flags & 1u) == 0;

@@ -1,0 +1,268 @@
+"""Batched, device-resident training step of the discriminative QBM.
+
+Mirrors ``Disc_QBM`` (src/model/faster_dqbm.py -- the class qbm_main.py runs -- and its loop twin
+src/model/discriminative_qbm.py): same constructor arguments, same parameter attribute names and
+shapes, same ``create_qubo_matrix_from`` / ``get_samples`` / ``train_for_one_iteration`` / ``predict``
+semantics, same learning rule ``param -= lr * (<.>_clamped - <.>_unclamped) / batch``.  What changes
+is the execution: the per-image Python loop (two ``sampler.sample`` calls per image, faster_dqbm.py:
+961-969) becomes one pass over the whole minibatch --
+
+    X, Y --(GEMM, f64)--> 2B QUBOs --K0--> spin models --K1--> 2B x reads chains --K3--> moments
+         --(small f64 GEMMs)--> parameter-shaped statistics --[all-reduce over ranks]--> SGD update
+
+all on the current CUDA stream without a host synchronisation until the loss is read back.
+
+``stats_mode`` selects which of the reference's two statistics functions is reproduced:
+  "loop"    discriminative_qbm.py:696-760 (works for one-hot labels and any sizes; trains W_hh)
+  "faster"  faster_dqbm.py:754-848 including its divergences (W_hh never
+            trained, output-output term doubled, binary labels and n_hidden <= dim_input only)
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from . import ising, sampler as _s
+
+
+def geomspace_device(lo: torch.Tensor, hi: torch.Tensor, num: int) -> torch.Tensor:
+    """np.geomspace along dim 1 on the device (same formula: 10 ** linspace(log10 lo, log10 hi), end
+    points pinned), float64 [B, num]."""
+    if num == 0:
+        return torch.zeros((lo.shape[0], 0), dtype=torch.float64, device=lo.device)
+    ls, le = torch.log10(lo), torch.log10(hi)
+    if num == 1:
+        return lo[:, None].clone()
+    step = (le - ls) / (num - 1)
+    y = torch.arange(num, dtype=torch.float64, device=lo.device)[None, :] * step[:, None] + ls[:, None]
+    y[:, -1] = le
+    out = torch.pow(torch.tensor(10.0, dtype=torch.float64, device=lo.device), y)
+    out[:, 0] = lo
+    out[:, -1] = hi
+    return out
+
+
+def schedule_device(rng: torch.Tensor, num_sweeps: int):
+    """Legacy neal beta range + geometric schedule from K0's ``range`` output ([B,2] = min non-zero
+    |bias|, max total |bias|); all-zero problems get neal's [0.1, 1.0].  Returns (betas f32 [B,nb], spb)."""
+    spb = int(max(1, num_sweeps // 1000.0))
+    nb = -(-num_sweeps // spb) if num_sweeps > 0 else 0
+    mn, mx = rng[:, 0], rng[:, 1]
+    empty = mx == 0
+    hot = torch.where(empty, torch.full_like(mx, 0.1), np.log(2) / torch.where(empty, torch.ones_like(mx), mx))
+    cold = torch.where(empty, torch.ones_like(mn), np.log(100) / torch.where(empty, torch.ones_like(mn), mn))
+    return geomspace_device(hot, cold, nb).to(torch.float32), spb
+
+
+class DiscQBM:
+    def __init__(self, dim_input, num_classes, epochs=2, n_hidden_nodes=4, seed=77, solver="SA", restricted=False,
+                 sample_count=20, anneal_steps=20, beta_eff=1, param_string="", load_path="", speicherort=None,
+                 parallelize=False, use_one_hot_encoding=False, use_old_parallization=True,
+                 stats_mode="faster", initial_states_generator="numpy", shared_stream=True, device=None,
+                 process_group=None):
+        if solver != "SA":
+            raise ValueError("the B200 path implements solver='SA' only (D-Wave / BMS paths are out of scope)")
+        if stats_mode not in ("loop", "faster"):
+            raise ValueError("stats_mode must be 'loop' or 'faster'")
+        self.epochs, self.seed = epochs, seed
+        self.dim_input, self.n_hidden_nodes = int(dim_input), int(n_hidden_nodes)
+        self.restricted, self.parallelize = bool(restricted), parallelize
+        self.use_one_hot_encoding = use_one_hot_encoding
+        self.n_output_nodes = int(num_classes) if use_one_hot_encoding else 1
+        self.solver_string = solver
+        self.sample_count, self.anneal_steps, self.beta_eff = int(sample_count), int(anneal_steps), beta_eff
+        self.param_string, self.load_path, self.speicherort = param_string, load_path, speicherort
+        self.stats_mode = stats_mode
+        self.initial_states_generator = initial_states_generator
+        self.shared_stream = shared_stream
+        self.device = _s._require_cuda(device)
+        self.pg = process_group
+        if stats_mode == "faster" and (self.n_output_nodes != 1 or self.n_hidden_nodes > self.dim_input):
+            # the reference's vectorised statistics raise for these shapes (Appendix B Q3)
+            raise ValueError("stats_mode='faster' reproduces faster_dqbm.py, which only runs for binary labels and "
+                             "n_hidden <= dim_input; use stats_mode='loop'")
+        # ---- parameter initialisation: same draws, same order as faster_dqbm.py:77-83,192-223 ----
+        h, no, di = self.n_hidden_nodes, self.n_output_nodes, self.dim_input
+        W_hh = None if restricted else np.triu(np.random.uniform(-1, 1, (h, h)), k=1)   # drawn BEFORE the reseed (Q12)
+        random.seed(seed)
+        np.random.seed(seed)
+        W_vh = np.random.uniform(-1, 1, (no + di, h))
+        W_vo = np.random.uniform(-1, 1, (di, no))
+        W_oo = np.triu(np.random.uniform(-1, 1, (no, no)), k=1)
+        b_h = np.random.uniform(-1, 1, h)
+        b_o = np.random.uniform(-1, 1, no)
+        self._p = {}
+        self.set_params(W_vh=W_vh, W_vo=W_vo, W_oo=W_oo, b_h=b_h, b_o=b_o, W_hh=W_hh)
+        self._init_cache = {}
+        self.nll_per_batch = []
+        self.step_count = 0
+        self.keep_samples = False
+        self.last_samples = None
+
+    # ---- parameters: device tensors, exposed under the reference's attribute names -------------
+    _NAMES = {"weights_all_visible_to_hidden": "W_vh", "weights_clamped_visible_to_output": "W_vo",
+              "weights_output_output": "W_oo", "biases_hidden": "b_h", "biases_output": "b_o",
+              "weights_hidden_hidden": "W_hh"}
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            self._p[k] = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device).clone()
+
+    def get_params(self) -> dict:
+        return {k: (None if v is None else v.cpu().numpy()) for k, v in self._p.items()}
+
+    def __getattr__(self, name):
+        names = type(self)._NAMES
+        if name in names and "_p" in self.__dict__:
+            v = self._p[names[name]]
+            return None if v is None else v.cpu().numpy()
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in type(self)._NAMES and "_p" in self.__dict__:
+            self.set_params(**{type(self)._NAMES[name]: value})
+        else:
+            object.__setattr__(self, name, value)
+
+    @property
+    def weight_objects(self):
+        p = self.get_params()
+        return [p["W_vh"], p["W_vo"], p["b_h"], p["b_o"], p["W_oo"], p["W_hh"]]
+
+    # ---- QUBO construction (faster_dqbm.py:225-284) ------------------------------------------------
+    def _labels(self, y_batch, B):
+        Y = torch.as_tensor(np.asarray(y_batch, dtype=np.float64)).to(self.device)
+        return Y.reshape(B, self.n_output_nodes)
+
+    def build_qubos(self, X: torch.Tensor, Y: torch.Tensor | None) -> torch.Tensor:
+        """Batched ``create_qubo_matrix_from``: float64 [B, n, n] on the device."""
+        p, no, h = self._p, self.n_output_nodes, self.n_hidden_nodes
+        B = X.shape[0]
+        if Y is not None:
+            diag = p["b_h"][None, :] + torch.cat((Y, X), dim=1) @ p["W_vh"]        # label rows first (:236)
+            Q = torch.diag_embed(diag)
+            if p["W_hh"] is not None:
+                Q = Q + p["W_hh"][None]
+        else:
+            n = no + h
+            upper = torch.zeros((n, n), dtype=torch.float64, device=self.device)
+            upper[:no, no:] += p["W_vh"][:no]
+            upper[:no, :no] += p["W_oo"]
+            if p["W_hh"] is not None:
+                upper[no:, no:] += p["W_hh"]
+            diag = torch.cat((p["b_o"], p["b_h"]))[None, :] + X @ torch.cat((p["W_vo"], p["W_vh"][no:]), dim=1)
+            Q = torch.diag_embed(diag) + upper[None]
+        return (Q / self.beta_eff).contiguous()
+
+    def create_qubo_matrix_from(self, input_vector, label=None) -> np.ndarray:
+        X = torch.as_tensor(np.asarray(input_vector, dtype=np.float64)).to(self.device)[None]
+        Y = None if label is None else self._labels(np.atleast_1d(label), 1)
+        return self.build_qubos(X, Y)[0].cpu().numpy()
+
+    # ---- sampling ---------------------------------------------------------------------------------
+    def _init_states(self, B, n):
+        if self.initial_states_generator == "philox":
+            return None
+        key = (self.sample_count, n)
+        if key not in self._init_cache:          # same RandomState(seed) draw for every call (Q6)
+            self._init_cache[key] = torch.from_numpy(ising.initial_states_numpy(self.seed, self.sample_count, n)).to(self.device)
+        return self._init_cache[key][None].expand(B, -1, -1).contiguous()
+
+    def sample_batch(self, Q: torch.Tensor, first_image: int = 0) -> torch.Tensor:
+        """int8 [B, sample_count, n] for a batch of QUBOs already on the device."""
+        B, n, _ = Q.shape
+        J, hh, _, rng = _s.qubo_to_ising_device(Q)
+        betas, spb = schedule_device(rng, self.anneal_steps)
+        flags = 2 if self.shared_stream else 0
+        off = 0 if self.shared_stream else first_image * self.sample_count
+        return _s.sa_sample(J, hh, betas, spb, self.sample_count, self.seed, chain_offset=off,
+                            init_states=self._init_states(B, n), flags=flags).states
+
+    def get_samples(self, input_vector, label=None) -> np.ndarray:
+        """One image: int8 [sample_count, n] (``np.vstack`` of the reference's list of sample views)."""
+        X = torch.as_tensor(np.asarray(input_vector, dtype=np.float64)).to(self.device)[None]
+        Y = None if label is None else self._labels(np.atleast_1d(label), 1)
+        return self.sample_batch(self.build_qubos(X, Y))[0].cpu().numpy()
+
+    # ---- statistics -> parameter-shaped errors (sums over the local images) -----------------------
+    def _errors(self, X, Y, mean_c, sec_c, mean_u, sec_u) -> dict:
+        no, h, di = self.n_output_nodes, self.n_hidden_nodes, self.dim_input
+        Mh_c, Mh_u, Mo_u = mean_c, mean_u[:, no:], mean_u[:, :no]
+        e = {}
+        e["b_h"] = (Mh_c - Mh_u).sum(dim=0)
+        e["b_o"] = (Y - Mo_u).sum(dim=0)
+        W = torch.zeros((no + di, h), dtype=torch.float64, device=self.device)
+        W[:di] = X.T @ (Mh_c - Mh_u)              # statistics rows: x first, then the label (Q1)
+        W[di:] = Y.T @ Mh_c
+        e["W_vh"] = W
+        e["W_vo"] = X.T @ (Y - Mo_u)
+        oo = torch.triu(Y.T @ Y - sec_u[:, :no, :no].sum(dim=0), diagonal=1)
+        if self.stats_mode == "faster" and not self.restricted:
+            oo = 2.0 * oo                          # faster_dqbm.py:831-845 adds the o-o term twice (Q2)
+        e["W_oo"] = oo
+        if not self.restricted:
+            if self.stats_mode == "loop":
+                e["W_hh"] = torch.triu(sec_c.sum(dim=0) - sec_u[:, no:, no:].sum(dim=0), diagonal=1)
+            else:
+                e["W_hh"] = torch.zeros((h, h), dtype=torch.float64, device=self.device)   # never accumulated (Q2)
+        return e
+
+    def train_for_one_iteration(self, x_batch, y_batch, learning_rate, nll=None, global_batch=None, first_image=0):
+        """faster_dqbm.py:998-1064 / discriminative_qbm.py:875-951 for a whole minibatch.  With a
+        process group, ``x_batch`` is this rank's shard, ``global_batch`` the minibatch size the errors
+        are divided by and ``first_image`` the shard's offset.  Returns (errors_biases_output, avg loss)."""
+        X = torch.as_tensor(np.asarray(x_batch, dtype=np.float64)).to(self.device)
+        B = X.shape[0]
+        Y = self._labels(y_batch, B)
+        Sc = self.sample_batch(self.build_qubos(X, Y), first_image)
+        Su = self.sample_batch(self.build_qubos(X, None), first_image)
+        mean_c, sec_c = _s.phase_stats(Sc, second=not self.restricted and self.stats_mode == "loop")
+        mean_u, sec_u = _s.phase_stats(Su, second=True)
+        err = self._errors(X, Y, mean_c, sec_c, mean_u, sec_u)
+        if self.keep_samples:
+            self.last_samples = (Sc, Su)
+        if self.stats_mode == "faster":
+            # NLL of output node 0 (faster_dqbm.py:972-994), float32 like torch.tensor(output_probs)
+            p1 = mean_u[:, 0].to(torch.float32)
+            lp = torch.log(torch.stack((1 - p1, p1), dim=1) + 1e-12)
+            loss_sum = -lp.gather(1, Y[:, :1].to(torch.int64)).sum().to(torch.float64)
+        else:
+            # discriminative_qbm.py:875-951 has its NLL commented out: total_nll_loss stays 0
+            loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
+        names = [k for k in ("b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh") if k in err]
+        flat = torch.cat([err[k].reshape(-1) for k in names] + [loss_sum.reshape(1)])
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        gb = float(global_batch if global_batch is not None else B)
+        pos = 0
+        for k in names:
+            cnt = err[k].numel()
+            self._p[k] -= learning_rate * (flat[pos:pos + cnt].reshape(err[k].shape) / gb)
+            if k == "b_o":
+                ebo = flat[pos:pos + cnt] / gb
+            pos += cnt
+        avg_loss = float(flat[-1].item() / gb)
+        self.nll_per_batch.append(avg_loss)
+        self.step_count += 1
+        return ebo.cpu().numpy(), avg_loss
+
+    # ---- prediction (faster_dqbm.py:1227-1241) ------------------------------------------------------
+    def predict_batch(self, X) -> np.ndarray:
+        Xd = torch.as_tensor(np.asarray(X, dtype=np.float64)).to(self.device)
+        Su = self.sample_batch(self.build_qubos(Xd, None))
+        mean_u, _ = _s.phase_stats(Su, second=False)
+        avg = mean_u[:, :self.n_output_nodes].cpu().numpy()
+        if self.use_one_hot_encoding:
+            return np.argmax(avg, axis=1)
+        return np.round(avg).astype(int)[:, 0]
+
+    def predict(self, data):
+        S = self.get_samples(data)
+        out = S[:, :self.n_output_nodes]
+        avg = np.mean(out, axis=0)
+        if self.use_one_hot_encoding:
+            return int(np.argmax(avg)), out.tolist()
+        return int(np.round(avg).astype(int)[0]), out.flatten()

@@ -1,0 +1,190 @@
+"""GPU: the sampler drop-ins (B1/B2) and the batched Disc_QBM training step against the oracle and
+the golden fixtures generated from the reference's own Python."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import random_qubo
+from oracle import model_oracle as M
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _replay_with_numpy_init(qbm, oracle, Q, reads, sweeps, seed):
+    h, J, _ = qbm.ising.qubo_to_ising(Q)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
+    init = qbm.ising.initial_states_numpy(seed, reads, Q.shape[0])
+    ref, _ = oracle.replay_sample(J[0].astype(np.float32), h[0].astype(np.float32), betas[0].astype(np.float32),
+                                  spb, seed, 0, reads, init01=init)
+    return ref
+
+
+def test_sample_Q_drop_in(qbm, oracle, cuda):
+    """Boundary B1: same constructor and call as LocalSASampler (src/qubo/sampler.py:19-33)."""
+    Q = random_qubo(41, seed=44, density=0.3)
+    s = qbm.B200SASampler(num_sweeps=300, seed=44)
+    out = s.sample_Q(Q, 25)
+    assert out.dtype == np.float32 and out.shape == (25, 41) and set(np.unique(out)) <= {0.0, 1.0}
+    assert np.array_equal(out, s.sample_Q(Q, 25))                       # deterministic function of Q (fixed seed)
+    assert np.array_equal(out.astype(np.int8), _replay_with_numpy_init(qbm, oracle, Q, 25, 300, 44))
+
+
+def test_neal_dimod_shims_end_to_end(qbm, oracle, cuda):
+    """Boundary B2: the call sequence of Disc_QBM.sample_sa (faster_dqbm.py:299-301,577,619)."""
+    qbm.shims.install()
+    try:
+        import dimod as di
+        from neal import SimulatedAnnealingSampler
+        Q = random_qubo(21, seed=77)
+        bqm = di.BQM(Q, "BINARY")
+        ss = SimulatedAnnealingSampler().sample(bqm, num_reads=30, num_sweeps=1000, seed=77)
+        samples = list(ss.samples())
+        assert len(samples) == 30
+        rows = np.vstack([np.array(list(s.values())) for s in samples])
+        assert rows.shape == (30, 21)
+        assert np.array_equal(ss.record.sample, _replay_with_numpy_init(qbm, oracle, Q, 30, 1000, 77))   # read order
+        assert np.allclose(ss.record.energy, oracle.qubo_energies(Q, ss.record.sample), rtol=1e-12, atol=1e-12)
+        assert np.all(np.diff([bqm.energy(s) for s in samples]) >= -1e-12)                                # energy order
+        assert ss.info["beta_schedule_type"] == "geometric" and len(ss.info["beta_range"]) == 2
+        # 20-sweep default of Disc_QBM (anneal_steps=20): 20 betas x 1 sweep
+        ss20 = SimulatedAnnealingSampler().sample(bqm, num_reads=5, num_sweeps=20, seed=1)
+        assert np.array_equal(ss20.record.sample, _replay_with_numpy_init(qbm, oracle, Q, 5, 20, 1))
+        # SPIN models and the dimod.Sampler siblings
+        sp = SimulatedAnnealingSampler().sample_ising({0: 0.5, 1: -0.2}, {(0, 1): -1.0}, num_reads=8, num_sweeps=50, seed=3)
+        assert set(np.unique(sp.record.sample)) <= {-1, 1}
+        assert np.allclose(sp.record.energy.min(), -1.3)
+        sq = SimulatedAnnealingSampler().sample_qubo({(0, 0): -1.0, (1, 1): -1.0, (0, 1): 3.0}, num_reads=8, num_sweeps=50, seed=3)
+        assert np.isclose(sq.record.energy.min(), -1.0)
+    finally:
+        qbm.shims.uninstall()
+
+
+@pytest.mark.parametrize("n,sweeps", [(24, 1000), (34, 1000), (193, 300), (522, 200)])
+def test_statistics_agree_with_neal_restatement(qbm, oracle, cuda, n, sweeps):
+    """north_star criterion 3: mean energy and ground-state hit rate of the kernel agree with the
+    reference sampler (the float64 xorshift restatement) within a stated statistical tolerance:
+    |mean energy difference| <= 4 standard errors + 0.2 % of |E_min|; hit-rate difference <= 0.12."""
+    Q = random_qubo(n, seed=1000 + n, density=0.9 if n == 193 else 1.0)
+    reads = 400
+    s_ref, e_ref = oracle.neal_sample(Q, reads, sweeps, seed=19)
+    smp, e_gpu, _ = qbm.sample_qubo_batch(Q, reads, sweeps, seed=19)
+    e_gpu = e_gpu[0]
+    emin = min(e_ref.min(), e_gpu.min())
+    se = np.sqrt(e_ref.var() / reads + e_gpu.var() / reads)
+    assert abs(e_ref.mean() - e_gpu.mean()) <= 4 * se + 2e-3 * abs(emin)
+    tol = 1e-6 * abs(emin)
+    assert abs(np.mean(e_ref <= emin + tol) - np.mean(e_gpu <= emin + tol)) <= 0.12
+
+
+def test_planted_ground_state_is_found(qbm, cuda):
+    """Gauge-transformed ferromagnet with known ground state: every read must find it."""
+    n = 96
+    rng = np.random.default_rng(5)
+    t = rng.choice([-1.0, 1.0], n)
+    g = np.abs(rng.normal(size=(n, n))) + 0.1
+    Jsp = -np.triu(g, 1) * np.outer(t, t)                       # spin couplings J_ij = -|g_ij| t_i t_j
+    # spin model -> QUBO (s = 2x - 1): Q_ij = 4 J_ij (i<j), Q_ii = -2 sum_j (J_ij + J_ji)
+    Q = 4 * Jsp
+    Q[np.arange(n), np.arange(n)] = -2 * (Jsp + Jsp.T).sum(axis=1)
+    smp, e, _ = qbm.sample_qubo_batch(Q, 64, 1000, seed=7)
+    x_t = ((t + 1) / 2).astype(np.int8)
+    ok = [np.array_equal(r, x_t) or np.array_equal(r, 1 - x_t) for r in smp[0]]
+    assert all(ok)
+
+
+def test_recorded_accuracy_through_the_gpu_sampler(qbm, cuda):
+    """End-to-end known answer: trained weights of the reference's own runs + the accuracy IT recorded
+    (out/paper_data/Pneumonia_param_doku/10_hnodes/*/test_val/e20_*_testacc_auc.pkl).  All 624 unclamped
+    QUBOs go through one batched launch (100 reads, 1000 sweeps, as in the runs); the majority output bit
+    must reproduce the recorded accuracy exactly."""
+    from sklearn.metrics import roc_auc_score
+    g = np.load(os.path.join(G, "pneumonia_h10_recorded_accuracy.npz"))
+    labels = g["labels"].astype(int)
+    for k in range(3):
+        off, diag = g[f"off_{k}"], g[f"diag_{k}"]
+        Q = off[None] + np.stack([np.diag(d) for d in diag])
+        smp, _, _ = qbm.sample_qubo_batch(Q, 100, 1000, seed=int(g[f"seed_{k}"]) % (2 ** 32), return_energy=False)
+        pred = np.round(smp[:, :, 0].mean(axis=1)).astype(int)              # predict(): np.round(mean)[0]
+        assert abs(np.mean(pred == labels) - float(g[f"acc_{k}"])) < 1e-12
+        assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12
+
+
+def _golden_params(g, prefix):
+    return {k: g[f"{prefix}_{k}"] for k in ("W_vh", "W_vo", "W_oo", "b_h", "b_o", "W_hh")}
+
+
+def test_disc_qbm_loop_training_step(qbm, cuda):
+    """T1/T3 (discriminative_qbm.py:696-760, 875-951), one-hot C1 shapes."""
+    g = np.load(os.path.join(G, "disc_qbm_loop_onehot.npz"))
+    np.random.seed(19)                                               # Appendix B Q12
+    m = qbm.DiscQBM(dim_input=16, num_classes=10, use_one_hot_encoding=True, n_hidden_nodes=24, restricted=False,
+                    sample_count=60, anneal_steps=200, beta_eff=1.0, seed=19, stats_mode="loop")
+    p0 = _golden_params(g, "w0")
+    for k, v in m.get_params().items():
+        assert np.array_equal(v, p0[k]), f"initial {k} differs from the reference's draw"
+    X, Y = g["X"], g["Y"]
+    Xd, Yd = torch.from_numpy(X).to(cuda), torch.from_numpy(Y).to(cuda)
+    assert np.allclose(m.build_qubos(Xd, Yd).cpu().numpy(), g["Qc"], rtol=0, atol=1e-13)
+    assert np.allclose(m.build_qubos(Xd, None).cpu().numpy(), g["Qu"], rtol=0, atol=1e-13)
+    assert np.allclose(m.create_qubo_matrix_from(X[1], Y[1]), g["Qc"][1], rtol=0, atol=1e-13)
+    m.keep_samples = True
+    _, loss = m.train_for_one_iteration(X, Y, float(g["lr"]))
+    assert loss == 0.0
+    Sc, Su = (t.cpu().numpy() for t in m.last_samples)
+    ref = M.disc_train_step(p0, X, Y, Sc, Su, float(g["lr"]), "loop")   # the reference's arithmetic on OUR samples
+    for k, v in m.get_params().items():
+        assert np.allclose(v, ref[k], rtol=0, atol=1e-12), k
+    # reference attribute names and shapes
+    assert m.weights_all_visible_to_hidden.shape == (26, 24) and m.weights_hidden_hidden.shape == (24, 24)
+    assert len(m.weight_objects) == 6
+    # sample sets are statistically the reference's: same ground states at these sizes
+    assert np.abs(Sc.mean(axis=1) - g["Sc"].astype(float).mean(axis=1)).mean() < 0.08
+    pred = m.predict_batch(X)
+    assert pred.shape == (4,)
+    one, outs = m.predict(X[0])
+    assert one == pred[0] and len(outs) == 60
+
+
+def test_disc_qbm_faster_training_step(qbm, cuda):
+    """T2/T3/T4 (faster_dqbm.py:754-848, 998-1064, 972-994) incl. the reference's quirks."""
+    g = np.load(os.path.join(G, "disc_qbm_faster_binary.npz"))
+    np.random.seed(44)
+    m = qbm.DiscQBM(dim_input=20, num_classes=2, use_one_hot_encoding=False, n_hidden_nodes=6, restricted=False,
+                    sample_count=50, anneal_steps=200, beta_eff=1.0, seed=44, stats_mode="faster")
+    p0 = _golden_params(g, "w0")
+    for k, v in m.get_params().items():
+        assert np.array_equal(v, p0[k])
+    X, Y = g["X"], g["Y"]
+    m.keep_samples = True
+    _, loss = m.train_for_one_iteration(X, Y, float(g["lr"]))
+    Sc, Su = (t.cpu().numpy() for t in m.last_samples)
+    ref = M.disc_train_step(p0, X, Y, Sc, Su, float(g["lr"]), "faster")
+    for k, v in m.get_params().items():
+        assert np.allclose(v, ref[k], rtol=0, atol=1e-12), k
+    assert np.array_equal(m.weights_hidden_hidden, p0["W_hh"])       # never trained (Appendix B Q2)
+    assert abs(loss - M.disc_nll(Su, Y)) < 1e-6
+    # with the reference's fixed per-call seed every image sees the same stream: shared_stream reproduces
+    # the per-image drop-in call exactly
+    s1 = m.get_samples(X[2], label=Y[2])
+    Q = m.create_qubo_matrix_from(X[2], Y[2])
+    s2 = qbm.B200SASampler(num_sweeps=200, seed=44).sample_Q(Q, 50)
+    # (device vs host spin conversion may differ in the last ulp of h; the trajectories still agree here)
+    assert np.mean(s1 == s2.astype(np.int8)) > 0.99
+    with pytest.raises(ValueError):
+        qbm.DiscQBM(dim_input=16, num_classes=10, use_one_hot_encoding=True, n_hidden_nodes=24, stats_mode="faster")
+
+
+def test_device_schedule_matches_numpy(qbm, cuda):
+    from qbm_b200.disc_qbm import schedule_device
+    Qs = np.stack([random_qubo(30, seed=s, scale=1 + 3 * s) for s in range(5)])
+    Qs[4] = 0.0
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    ref, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), 1000)
+    _, _, _, rng = qbm.qubo_to_ising_device(torch.from_numpy(Qs).to(cuda))
+    got, spb2 = schedule_device(rng, 1000)
+    assert spb == spb2 and got.shape == (5, 1000)
+    assert np.allclose(got.cpu().numpy(), ref.astype(np.float32), rtol=3e-7, atol=0)
+    assert got[4, 0].item() == np.float32(0.1) and got[4, -1].item() == 1.0
