@@ -108,6 +108,52 @@ int qbm_phase_stats(const int8_t *states, long long batch_q, long long R, int n,
                     double *second_out, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K4  TF32 tensor-core GEMM (tcgen05 + TMEM + TMA):  C[M,N] = act(alpha * A[M,K] . B[N,K]^T + bias_n) + beta * Cin
+ * ref: torch.matmul / expand-mul-sum in src/ClassificationRBM.py:44-56,106,118-128.
+ *   A [M, lda], B [N, ldb] row-major float32 with K contiguous; lda, ldb multiples of 4, 16-byte aligned
+ *   act: 0 identity, 1 sigmoid;  bias_n [N], Cin [M, ldcin] nullable;  C [M, ldc] and/or Ct [N, ldct] (= C^T)
+ */
+int qbm_gemm_tf32(const float *A, long long lda, const float *B, long long ldb, int M, int N, int K,
+                  float alpha, float beta, const float *Cin, long long ldcin, const float *bias_n, int act,
+                  float *C, long long ldc, float *Ct, long long ldct, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4/K5  ClassificationRBM (ref: src/ClassificationRBM.py).  Storage contract: every matrix is
+ * row-major float32 with leading dimension ld4(cols) = (cols + 3) & ~3:
+ *   W [V, ld4(H)]  (:26 weights), Wt [H, ld4(V)] = W^T (kept in sync by the step functions),
+ *   U [C, ld4(H)]  (:30 class_weights), b_v [V], b_h [H], b_c [C], x / v [B, ld4(V)], hid [B, ld4(H)],
+ *   y int32 [B], probabilities over classes [B, ld4(C)].  C <= 32.
+ * qbm_rbm_sample_hidden   :43-47   P[B, ld4(H)] = sigmoid(v W + b_h + U[y])
+ * qbm_rbm_sample_visible  :49-52   P[B, ld4(V)] = sigmoid(hid W^T + b_v)
+ * qbm_rbm_sample_class    :54-60   P[B, ld4(C)] = L1-normalised exp(hid U^T + b_c)
+ * qbm_rbm_class_given_x   :62-86   P[B, ld4(C)] = p(y|x)
+ * qbm_rbm_disc_step       :101-146 + :88-99  exact discriminative gradient step, in place;
+ *                         probs [B, ld4(C)], pred int32 [B] (nullable), loss float[1] (nullable; the
+ *                         reference's CrossEntropyLoss applied to the probabilities, :142)
+ * qbm_rbm_cd1_step        CD-1 composed from the three primitives (the reference stores k and the
+ *                         primitives but never wires them): h0 ~ Bern(ph0), v1 ~ Bern,
+ *                         y1 ~ Cat, dW = v0^T ph0 - v1^T ph1, ...; Philox keyed by (seed, step)
+ * workspace: qbm_rbm_workspace_bytes(B, V, H, C) bytes, 16-byte aligned.
+ */
+size_t qbm_rbm_workspace_bytes(int B, int V, int H, int C);
+int qbm_rbm_sample_hidden(const float *Wt, const float *U, const float *b_h, const float *v, const int *y,
+                          int B, int V, int H, int C, float *P, void *stream);
+int qbm_rbm_sample_visible(const float *W, const float *b_v, const float *hid, int B, int V, int H, float *P,
+                           void *stream);
+int qbm_rbm_sample_class(const float *U, const float *b_c, const float *hid, int B, int H, int C, float *P,
+                         void *stream);
+int qbm_rbm_class_given_x(const float *Wt, const float *U, const float *b_h, const float *b_c, const float *x,
+                          int B, int V, int H, int C, float *P, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *x,
+                      const int *y, int B, int V, int H, int C, float lr, float factor, float sparse_constant,
+                      float *probs, int *pred, float *loss, void *workspace, size_t workspace_bytes, void *stream);
+int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                     const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                     unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that
  * tests can compare them bit-for-bit with the oracle's independent C restatement.
  *   qbm_test_philox: ctr [count,4] u32, key [count,2] u32 -> out [count,4] u32

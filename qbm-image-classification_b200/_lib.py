@@ -36,6 +36,15 @@ SIGNATURES = {
     "qbm_qubo_energy": (_c_i, [_c_p, _c_i, _c_ll, _c_p, _c_ll, _c_p, _c_p]),
     "qbm_phase_stats_workspace_bytes": (_c_sz, [_c_ll, _c_ll, _c_i]),
     "qbm_phase_stats": (_c_i, [_c_p, _c_ll, _c_ll, _c_i, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "qbm_gemm_tf32": (_c_i, [_c_p, _c_ll, _c_p, _c_ll, _c_i, _c_i, _c_i, ctypes.c_float, ctypes.c_float, _c_p, _c_ll, _c_p,
+                             _c_i, _c_p, _c_ll, _c_p, _c_ll, _c_p]),
+    "qbm_rbm_workspace_bytes": (_c_sz, [_c_i, _c_i, _c_i, _c_i]),
+    "qbm_rbm_sample_hidden": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p]),
+    "qbm_rbm_sample_visible": (_c_i, [_c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_p, _c_p]),
+    "qbm_rbm_sample_class": (_c_i, [_c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_p, _c_p]),
+    "qbm_rbm_class_given_x": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_sz, _c_p]),
+    "qbm_rbm_disc_step": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [ctypes.c_float] * 3 + [_c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "qbm_rbm_cd1_step": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [ctypes.c_float] * 2 + [_c_u64, _c_u, _c_p, _c_sz, _c_p]),
     "qbm_test_philox": (_c_i, [_c_p, _c_p, _c_p, _c_ll, _c_p]),
     "qbm_test_exp": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
 }

@@ -1,0 +1,399 @@
+// K5 + step orchestration for the ClassificationRBM (src/ClassificationRBM.py:43-157).
+//
+// The dense contractions (x.W, h.W^T, x^T.D) run on the tcgen05 TF32 GEMM (gemm_tcgen05.cu) with
+// bias / class-bias / sigmoid / Bernoulli / SGD-accumulate fused into its epilogue; everything that is
+// O(B*H*C) (softplus sums, p(y|x), the positive-minus-negative phase difference, class-weight and bias
+// gradients) is fused elementwise work here.  Storage contract: every matrix is row-major with its
+// leading dimension rounded up to a multiple of 4 floats (16-byte rows for TMA): ld(X) = (cols+3)&~3.
+#include "gemm.cuh"
+
+namespace {
+
+__host__ __device__ inline long long ld4(long long cols) { return (cols + 3) & ~3LL; }
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float softplus(float z) { return fmaxf(z, 0.0f) + log1pf(__expf(-fabsf(z))); }
+
+constexpr int MAXC = 32;
+
+// out[c][r] = in[r][c]
+__global__ void transpose_kernel(const float *__restrict__ in, long long ldi, float *__restrict__ out, long long ldo,
+                                 int rows, int cols)
+{
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ldi + c] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (c < cols && r < rows) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
+    }
+}
+
+// p(y|x) per row (ClassificationRBM.py:62-86) and, when Dt != null, the phase difference
+// D[b,h] = o[b,h,y_b] - sum_c p[b,c] o[b,h,c]  with o = sigmoid(A[b,h] + U[c,h])   (:106-128), stored transposed.
+__global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ U,
+                                                      long long ldu, const float *__restrict__ b_c, const int *__restrict__ y,
+                                                      int H, int C, float *__restrict__ P, long long ldp,
+                                                      float *__restrict__ Dt, long long lddt)
+{
+    __shared__ float red[MAXC][8];
+    __shared__ float prob[MAXC];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *Ab = A + (size_t)b * lda;
+    float sp[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) sp[c] = 0.0f;
+    for (int h = tid; h < H; h += 256) {
+        const float a = Ab[h];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < C) sp[c] += softplus(a + __ldg(U + (size_t)c * ldu + h));
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+            float v = sp[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[c][warp] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float s[MAXC], mx = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            float v = b_c[c];
+            for (int w = 0; w < 8; ++w) v += red[c][w];
+            s[c] = v; mx = fmaxf(mx, v);
+        }
+        float z = 0.0f;
+        for (int c = 0; c < C; ++c) { s[c] = __expf(s[c] - mx); z += s[c]; }
+        for (int c = 0; c < C; ++c) { prob[c] = s[c] / z; P[(size_t)b * ldp + c] = prob[c]; }
+    }
+    if (Dt == nullptr) return;
+    __syncthreads();
+    const int yb = y[b];
+    for (int h = tid; h < H; h += 256) {
+        const float a = Ab[h];
+        float pos = 0.0f, neg = 0.0f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+                const float o = sigm(a + __ldg(U + (size_t)c * ldu + h));
+                neg += prob[c] * o;
+                if (c == yb) pos = o;
+            }
+        }
+        Dt[(size_t)h * lddt + b] = pos - neg;
+    }
+}
+
+// class-weight / hidden-bias gradients of the discriminative step and their SGD update (:88-99,120-136)
+__global__ void rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U, long long ldu,
+                                       float *__restrict__ b_h, const float *__restrict__ P, long long ldp,
+                                       const int *__restrict__ y, const float *__restrict__ Dt, long long lddt,
+                                       int B, int H, float scale, float sparse)
+{
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (h >= H) return;
+    const float u = U[(size_t)c * ldu + h];
+    float g = 0.0f;
+    for (int b = 0; b < B; ++b) {
+        const float o = sigm(A[(size_t)b * lda + h] + u);
+        g += (y[b] == c ? o : 0.0f) - P[(size_t)b * ldp + c] * o;
+    }
+    U[(size_t)c * ldu + h] = u + scale * g;
+    if (c == 0) {
+        float gb = 0.0f;
+        for (int b = 0; b < B; ++b) gb += Dt[(size_t)h * lddt + b];
+        b_h[h] = b_h[h] + scale * gb - sparse;
+    }
+}
+
+// class-bias update, visible-bias decay, loss (CrossEntropyLoss applied to probabilities, :142) and argmax
+__global__ void rbm_disc_finish_kernel(float *__restrict__ b_c, float *__restrict__ b_v, const float *__restrict__ P,
+                                       long long ldp, const int *__restrict__ y, int B, int C, int V, float scale,
+                                       float sparse, int *__restrict__ pred, float *__restrict__ loss, int update)
+{
+    __shared__ float red[256];
+    const int tid = threadIdx.x;
+    float l = 0.0f;
+    for (int b = tid; b < B; b += blockDim.x) {
+        const float *p = P + (size_t)b * ldp;
+        float z = 0.0f, best = -1.0f; int arg = 0;
+        for (int c = 0; c < C; ++c) { z += __expf(p[c]); if (p[c] > best) { best = p[c]; arg = c; } }
+        l += __logf(z) - p[y[b]];
+        if (pred != nullptr) pred[b] = arg;
+    }
+    red[tid] = l;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    if (tid == 0 && loss != nullptr) loss[0] = red[0] / (float)B;
+    if (!update) return;
+    if (tid < C) {
+        float g = 0.0f;
+        for (int b = 0; b < B; ++b) g += (y[b] == tid ? 1.0f : 0.0f) - P[(size_t)b * ldp + tid];
+        b_c[tid] = b_c[tid] + scale * g - sparse;
+    }
+    if (sparse != 0.0f)
+        for (int v = tid; v < V; v += blockDim.x) b_v[v] -= sparse;
+}
+
+// p(y|h) = exp(h.U^T + b_c) L1-normalised (:54-60) and, when y1 != null, a categorical sample of it
+__global__ void __launch_bounds__(128) rbm_class_kernel(const float *__restrict__ Hm, long long ldh, const float *__restrict__ U,
+                                                       long long ldu, const float *__restrict__ b_c, int H, int C,
+                                                       float *__restrict__ P, long long ldp, int *__restrict__ y1,
+                                                       unsigned long long seed, unsigned int stream)
+{
+    __shared__ float red[MAXC][4];
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = 0.0f;
+    for (int h = tid; h < H; h += 128) {
+        const float hv = Hm[(size_t)b * ldh + h];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+            if (c < C) acc[c] += hv * __ldg(U + (size_t)c * ldu + h);
+    }
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) {
+            float v = acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[c][warp] = v;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float e[MAXC], z = 0.0f;
+        for (int c = 0; c < C; ++c) { e[c] = __expf(red[c][0] + red[c][1] + red[c][2] + red[c][3] + b_c[c]); z += e[c]; }
+        z = fmaxf(z, 1e-12f);                                   // torch.nn.functional.normalize eps
+        float cum = 0.0f; int pick = C - 1; bool done = false;
+        const Philox4 u4 = philox4x32_10((uint32_t)b, 0u, stream, 0x434C53u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const float u = (float)(u4.x >> 8) * 5.9604644775390625e-8f;
+        for (int c = 0; c < C; ++c) {
+            const float p = e[c] / z;
+            if (P != nullptr) P[(size_t)b * ldp + c] = p;
+            cum += p;
+            if (!done && u < cum) { pick = c; done = true; }
+        }
+        if (y1 != nullptr) y1[b] = pick;
+    }
+}
+
+// CD-1 gradients of the small parameters from transposed activations ([., B] rows are contiguous over b)
+__global__ void rbm_cd_small_update_kernel(const float *__restrict__ v0t, const float *__restrict__ v1t, long long ldvt,
+                                           const float *__restrict__ p0t, const float *__restrict__ p1t, long long ldpt,
+                                           const int *__restrict__ y0, const int *__restrict__ y1, float *__restrict__ U,
+                                           long long ldu, float *__restrict__ b_v, float *__restrict__ b_h,
+                                           float *__restrict__ b_c, int B, int V, int H, int C, float scale, float sparse)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < V) {
+        float g = 0.0f;
+        for (int b = 0; b < B; ++b) g += v0t[(size_t)i * ldvt + b] - v1t[(size_t)i * ldvt + b];
+        b_v[i] = b_v[i] + scale * g - sparse;
+    }
+    if (i < H) {
+        float g = 0.0f;
+        for (int b = 0; b < B; ++b) g += p0t[(size_t)i * ldpt + b] - p1t[(size_t)i * ldpt + b];
+        b_h[i] = b_h[i] + scale * g - sparse;
+        for (int c = 0; c < C; ++c) {
+            float gu = 0.0f;
+            for (int b = 0; b < B; ++b)
+                gu += (y0[b] == c ? p0t[(size_t)i * ldpt + b] : 0.0f) - (y1[b] == c ? p1t[(size_t)i * ldpt + b] : 0.0f);
+            U[(size_t)c * ldu + i] += scale * gu;
+        }
+    }
+    if (i < C) {
+        float g = 0.0f;
+        for (int b = 0; b < B; ++b) g += (y0[b] == i ? 1.0f : 0.0f) - (y1[b] == i ? 1.0f : 0.0f);
+        b_c[i] = b_c[i] + scale * g - sparse;
+    }
+}
+
+int transpose(const float *in, long long ldi, float *out, long long ldo, int rows, int cols, cudaStream_t st)
+{
+    transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, st>>>(in, ldi, out, ldo, rows, cols);
+    QBM_LAUNCH_OK("transpose_kernel");
+    return QBM_OK;
+}
+
+struct Ws {   // carve-up of the caller's workspace (floats)
+    float *A, *P, *Dt, *xt, *p0, *p0t, *h0, *v1, *v1t, *p1t, *pc;
+    int *y1;
+};
+
+size_t ws_floats(int B, int V, int H, int C)
+{
+    const size_t lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    // A[B,lH] P[B,lC] Dt[H,lB] xt[V,lB] p0[B,lH] p0t[H,lB] h0[B,lH] v1[B,lV] v1t[V,lB] p1t[H,lB] pc[B,lC] y1[B]
+    return (size_t)B * lH * 3 + (size_t)B * lC * 2 + (size_t)H * lB * 3 + (size_t)V * lB * 2 + (size_t)B * lV + lB + 64;
+}
+
+Ws carve(void *workspace, int B, int V, int H, int C)
+{
+    const size_t lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    float *p = reinterpret_cast<float *>(workspace);
+    Ws w;
+    auto take = [&](size_t n) { float *r = p; p += (n + 3) & ~size_t(3); return r; };
+    w.A = take((size_t)B * lH); w.P = take((size_t)B * lC); w.Dt = take((size_t)H * lB); w.xt = take((size_t)V * lB);
+    w.p0 = take((size_t)B * lH); w.p0t = take((size_t)H * lB); w.h0 = take((size_t)B * lH); w.v1 = take((size_t)B * lV);
+    w.v1t = take((size_t)V * lB); w.p1t = take((size_t)H * lB); w.pc = take((size_t)B * lC);
+    w.y1 = reinterpret_cast<int *>(take(lB));
+    return w;
+}
+
+int check_dims(const char *who, int B, int V, int H, int C)
+{
+    if (B < 1 || V < 1 || H < 1 || C < 1 || C > MAXC) {
+        qbm_set_error("%s: need B, V, H >= 1 and 1 <= C <= %d (B=%d V=%d H=%d C=%d)", who, B, V, H, C, MAXC);
+        return QBM_EINVAL;
+    }
+    return QBM_OK;
+}
+
+}  // namespace
+
+extern "C" QBM_API size_t qbm_rbm_workspace_bytes(int B, int V, int H, int C)
+{
+    if (B < 1 || V < 1 || H < 1 || C < 1) return 0;
+    return ws_floats(B, V, H, C) * sizeof(float);
+}
+
+// R1 (:43-47): P[B, ld4(H)] = sigmoid(v.W + b_h + U[y]);  Wt = W^T [H, ld4(V)]
+extern "C" QBM_API int qbm_rbm_sample_hidden(const float *Wt, const float *U, const float *b_h, const float *v, const int *y,
+                                             int B, int V, int H, int C, float *P, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_sample_hidden", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(Wt && U && b_h && v && y && P, "qbm_rbm_sample_hidden: null pointer argument");
+    EpiParams ep = {};
+    ep.C = P; ep.ldc = ld4(H); ep.bias_n = b_h; ep.rowtab = U; ep.ridx = y; ep.ldtab = ld4(H); ep.alpha = 1.0f; ep.act = 1;
+    return qbm_gemm_tf32_launch(v, ld4(V), Wt, ld4(V), B, H, V, ep, (cudaStream_t)stream);
+}
+
+// R2 (:49-52): P[B, ld4(V)] = sigmoid(h.W^T + b_v);  W [V, ld4(H)]
+extern "C" QBM_API int qbm_rbm_sample_visible(const float *W, const float *b_v, const float *hid, int B, int V, int H,
+                                              float *P, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_sample_visible", B, V, H, 1)) return rc;
+    QBM_CHECK_ARG(W && b_v && hid && P, "qbm_rbm_sample_visible: null pointer argument");
+    EpiParams ep = {};
+    ep.C = P; ep.ldc = ld4(V); ep.bias_n = b_v; ep.alpha = 1.0f; ep.act = 1;
+    return qbm_gemm_tf32_launch(hid, ld4(H), W, ld4(H), B, V, H, ep, (cudaStream_t)stream);
+}
+
+// R3 (:54-60): P[B, ld4(C)] = normalize_L1(exp(h.U^T + b_c))
+extern "C" QBM_API int qbm_rbm_sample_class(const float *U, const float *b_c, const float *hid, int B, int H, int C, float *P,
+                                            void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_sample_class", B, 1, H, C)) return rc;
+    QBM_CHECK_ARG(U && b_c && hid && P, "qbm_rbm_sample_class: null pointer argument");
+    rbm_class_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(hid, ld4(H), U, ld4(H), b_c, H, C, P, ld4(C), nullptr, 0ull, 0u);
+    QBM_LAUNCH_OK("rbm_class_kernel");
+    return QBM_OK;
+}
+
+// p(y|x) (:62-86): P[B, ld4(C)]; workspace as for the steps
+extern "C" QBM_API int qbm_rbm_class_given_x(const float *Wt, const float *U, const float *b_h, const float *b_c, const float *x,
+                                             int B, int V, int H, int C, float *P, void *workspace, size_t workspace_bytes,
+                                             void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_class_given_x", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(Wt && U && b_h && b_c && x && P && workspace, "qbm_rbm_class_given_x: null pointer argument");
+    if (workspace_bytes < qbm_rbm_workspace_bytes(B, V, H, C)) { qbm_set_error("qbm_rbm_class_given_x: workspace too small"); return QBM_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = carve(workspace, B, V, H, C);
+    EpiParams ep = {};
+    ep.C = w.A; ep.ldc = ld4(H); ep.bias_n = b_h; ep.alpha = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(x, ld4(V), Wt, ld4(V), B, H, V, ep, st)) return rc;
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, ld4(H), U, ld4(H), b_c, nullptr, H, C, P, ld4(C), nullptr, 0);
+    QBM_LAUNCH_OK("rbm_rows_kernel");
+    return QBM_OK;
+}
+
+// R4 + R5 (:101-146, :88-99): one discriminative training step, parameters updated in place.
+//   W [V, ld4(H)], Wt [H, ld4(V)] (kept equal to W^T), U [C, ld4(H)], b_v [V], b_h [H], b_c [C],
+//   x [B, ld4(V)], y int32 [B]; outputs probs [B, ld4(C)], pred int32 [B] (nullable), loss [1] (nullable)
+extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *x,
+                                         const int *y, int B, int V, int H, int C, float lr, float factor,
+                                         float sparse_constant, float *probs, int *pred, float *loss, void *workspace,
+                                         size_t workspace_bytes, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_disc_step", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && x && y && probs && workspace, "qbm_rbm_disc_step: null pointer argument");
+    if (workspace_bytes < qbm_rbm_workspace_bytes(B, V, H, C)) { qbm_set_error("qbm_rbm_disc_step: workspace too small"); return QBM_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = carve(workspace, B, V, H, C);
+    const long long lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    const float scale = factor * lr / (float)B;
+    // A = x.W + b_h
+    EpiParams e1 = {};
+    e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
+    // p(y|x) and D^T
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB);
+    QBM_LAUNCH_OK("rbm_rows_kernel");
+    if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
+    // class weights / hidden bias (reads the pre-update A, U), then class bias, loss, argmax
+    rbm_disc_update_kernel<<<dim3((H + 127) / 128, C), 128, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
+                                                                   sparse_constant);
+    QBM_LAUNCH_OK("rbm_disc_update_kernel");
+    rbm_disc_finish_kernel<<<1, 256, 0, st>>>(b_c, b_v, probs, lC, y, B, C, V, scale, sparse_constant, pred, loss, 1);
+    QBM_LAUNCH_OK("rbm_disc_finish_kernel");
+    // W += scale * x^T.D   (SGD update fused into the GEMM epilogue), then refresh W^T
+    EpiParams e2 = {};
+    e2.C = W; e2.ldc = lH; e2.Cin = W; e2.ldcin = lH; e2.alpha = scale; e2.beta = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.Dt, lB, V, H, B, e2, st)) return rc;
+    return transpose(W, lH, Wt, lV, V, H, st);
+}
+
+// CD-1 step composed from the primitives:
+//   h0 ~ Bern(R1(v0,y0)); v1 ~ Bern(R2(h0)); y1 ~ Cat(R3(h0)); ph1 = R1(v1,y1);
+//   dW = v0^T ph0 - v1^T ph1; dU = y0^T ph0 - y1^T ph1; db_v = sum(v0-v1); db_h = sum(ph0-ph1); db_c = sum(y0-y1)
+extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                                        const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                                        unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
+                                        void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_cd1_step", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && v0 && y0 && workspace, "qbm_rbm_cd1_step: null pointer argument");
+    if (workspace_bytes < qbm_rbm_workspace_bytes(B, V, H, C)) { qbm_set_error("qbm_rbm_cd1_step: workspace too small"); return QBM_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = carve(workspace, B, V, H, C);
+    const long long lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    const float scale = lr / (float)B;
+    // positive phase: ph0 (+ transposed), h0 ~ Bernoulli(ph0)
+    EpiParams e = {};
+    e.C = w.p0; e.ldc = lH; e.Ct = w.p0t; e.ldct = lB; e.S = w.h0; e.lds = lH; e.bias_n = b_h; e.rowtab = U; e.ridx = y0;
+    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u;
+    if (int rc = qbm_gemm_tf32_launch(v0, lV, Wt, lV, B, H, V, e, st)) return rc;
+    // negative phase: v1 ~ Bernoulli(sigmoid(h0.W^T + b_v)) (+ transposed), y1 ~ Cat(p(y|h0))
+    EpiParams e2 = {};
+    e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
+    e2.stream = step * 4u + 1u;
+    if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u);
+    QBM_LAUNCH_OK("rbm_class_kernel");
+    EpiParams e3 = {};
+    e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
+    if (int rc = qbm_gemm_tf32_launch(w.v1, lV, Wt, lV, B, H, V, e3, st)) return rc;
+    if (int rc = transpose(v0, lV, w.xt, lB, B, V, st)) return rc;
+    // small parameters, then W += scale (v0^T ph0 - v1^T ph1) fused into two GEMM epilogues, then W^T
+    const int mx = V > H ? V : H;
+    rbm_cd_small_update_kernel<<<(mx + 127) / 128, 128, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, U, lH, b_v, b_h,
+                                                                b_c, B, V, H, C, scale, sparse_constant);
+    QBM_LAUNCH_OK("rbm_cd_small_update_kernel");
+    EpiParams g1 = {};
+    g1.C = W; g1.ldc = lH; g1.Cin = W; g1.ldcin = lH; g1.alpha = scale; g1.beta = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.p0t, lB, V, H, B, g1, st)) return rc;
+    g1.alpha = -scale;
+    if (int rc = qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st)) return rc;
+    return transpose(W, lH, Wt, lV, V, H, st);
+}

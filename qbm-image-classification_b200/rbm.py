@@ -1,0 +1,208 @@
+"""Boundary B3: ``ClassificationRBM`` with the reference's attribute names,
+shapes and method signatures (src/ClassificationRBM.py:12-157), executed by the tcgen05 GEMM and the
+fused elementwise kernels of libqbm_b200.so.
+
+Reference attributes ``weights [V,H]``, ``visible_bias [V]``, ``hidden_bias [H]``, ``class_weights [C,H]``,
+``class_bias [C]`` are float32 CUDA tensors (views into 16-byte-row padded storage).  Methods:
+
+* ``sample_hidden(v, y_onehot)`` / ``sample_visible(h)`` / ``sample_class(h)``   (:43-60)
+* ``sample_class_given_x(x)``                                                   (:62-86)
+* ``discriminative_training(x, y, factor=1) -> (error, predicted, class_probabilities)``  (:101-146)
+* ``cd1_training(v0, y0)`` -- the CD-1 step assembled from the three primitives (the reference keeps
+  ``k`` and the primitives but never wires them)
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .sampler import _require_cuda, _stream_ptr
+
+
+def _ld4(c: int) -> int:
+    return (c + 3) & ~3
+
+
+def _padded(rows: int, cols: int, dev) -> torch.Tensor:
+    return torch.zeros((rows, _ld4(cols)), dtype=torch.float32, device=dev)
+
+
+def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha=1.0, beta=0.0, Cin=None, bias=None, act=0, want_transposed=False):
+    """C = act(alpha * A @ B.T + bias) + beta * Cin on the tcgen05 TF32 pipeline (A [M,K], B [N,K], K % 4 == 0)."""
+    L = _lib.load()
+    assert A.is_cuda and B.is_cuda and A.dtype == torch.float32 and B.dtype == torch.float32
+    A = A.contiguous(); B = B.contiguous()
+    M, K = A.shape
+    N = B.shape[0]
+    C = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    Ct = torch.empty((N, M), dtype=torch.float32, device=A.device) if want_transposed else None
+    if Cin is not None:
+        Cin = Cin.contiguous()
+    with torch.cuda.device(A.device):
+        rc = L.qbm_gemm_tf32(A.data_ptr(), K, B.data_ptr(), K, M, N, K, float(alpha), float(beta),
+                             Cin.data_ptr() if Cin is not None else None, N, bias.data_ptr() if bias is not None else None,
+                             int(act), C.data_ptr(), N, Ct.data_ptr() if Ct is not None else None, M, _stream_ptr(A.device))
+    _lib.check(rc)
+    return (C, Ct) if want_transposed else C
+
+
+class B200ClassificationRBM:
+    def __init__(self, num_visible, num_hidden, k, num_classes=2, learning_rate=0.05, sparse_constant=0.00,
+                 use_cuda=True, seed=42, device=None):
+        # same RNG protocol as the reference (:14-15, :26-30): CPU generators, then moved to the device
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        self.seed = seed
+        self.num_visible, self.num_hidden, self.k = int(num_visible), int(num_hidden), k
+        self.learning_rate = learning_rate
+        self.use_cuda = True
+        self.num_classes = int(num_classes)
+        self.sparse_constant = sparse_constant
+        if self.num_classes > 32:
+            raise ValueError("the fused class kernels support at most 32 classes")
+        self.device = _require_cuda(device)
+        V, H, C = self.num_visible, self.num_hidden, self.num_classes
+        w = torch.randn(V, H) * 0.1
+        self._W = _padded(V, H, self.device); self._W[:, :H] = w.to(self.device)
+        self._Wt = _padded(H, V, self.device); self._Wt[:, :V] = w.t().to(self.device)
+        self._U = _padded(C, H, self.device)
+        self.visible_bias = (torch.ones(V) * 0.5).to(self.device)
+        self.hidden_bias = torch.zeros(H, device=self.device)
+        self.class_bias = torch.zeros(C, device=self.device)
+        self._ws = None
+        self._ws_key = None
+        self._step = 0
+        self.acc_per_epoch_list = []
+        self.auc_per_epoch_list = []
+
+    # ---- reference attribute names ---------------------------------------------------------------
+    @property
+    def weights(self):
+        return self._W[:, :self.num_hidden]
+
+    @weights.setter
+    def weights(self, w):
+        w = torch.as_tensor(w, dtype=torch.float32).to(self.device)
+        self._W.zero_(); self._W[:, :self.num_hidden] = w
+        self._Wt.zero_(); self._Wt[:, :self.num_visible] = w.t()
+
+    @property
+    def class_weights(self):
+        return self._U[:, :self.num_hidden]
+
+    @class_weights.setter
+    def class_weights(self, u):
+        self._U.zero_(); self._U[:, :self.num_hidden] = torch.as_tensor(u, dtype=torch.float32).to(self.device)
+
+    # ---- helpers ------------------------------------------------------------------------------------
+    def _workspace(self, B):
+        key = B
+        if self._ws_key != key:
+            L = _lib.load()
+            nbytes = L.qbm_rbm_workspace_bytes(B, self.num_visible, self.num_hidden, self.num_classes)
+            self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    def _pad_rows(self, x, cols):
+        x = torch.as_tensor(x, dtype=torch.float32).to(self.device)
+        if x.dim() != 2 or x.shape[1] != cols:
+            raise ValueError(f"expected a [B, {cols}] matrix, got {tuple(x.shape)}")
+        if cols == _ld4(cols) and x.is_contiguous():
+            return x
+        out = _padded(x.shape[0], cols, self.device)
+        out[:, :cols] = x
+        return out
+
+    def _labels(self, y, B):
+        y = torch.as_tensor(y).to(self.device)
+        if y.dim() == 2:                       # one-hot rows, as sample_hidden receives them
+            y = y.argmax(dim=1)
+        if y.shape != (B,):
+            raise ValueError(f"expected {B} labels, got shape {tuple(y.shape)}")
+        return y.to(torch.int32).contiguous()
+
+    def _call(self, fn, *args):
+        with torch.cuda.device(self.device):
+            rc = fn(*args, _stream_ptr(self.device))
+        _lib.check(rc)
+
+    # ---- Gibbs primitives (:43-60) --------------------------------------------------------------------
+    def sample_hidden(self, visible_activations, class_activations):
+        L = _lib.load()
+        v = self._pad_rows(visible_activations, self.num_visible)
+        B = v.shape[0]
+        y = self._labels(class_activations, B)
+        P = _padded(B, self.num_hidden, self.device)
+        self._call(L.qbm_rbm_sample_hidden, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(), v.data_ptr(),
+                   y.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, P.data_ptr())
+        return P[:, :self.num_hidden]
+
+    def sample_visible(self, hidden_activations):
+        L = _lib.load()
+        h = self._pad_rows(hidden_activations, self.num_hidden)
+        B = h.shape[0]
+        P = _padded(B, self.num_visible, self.device)
+        self._call(L.qbm_rbm_sample_visible, self._W.data_ptr(), self.visible_bias.data_ptr(), h.data_ptr(), B,
+                   self.num_visible, self.num_hidden, P.data_ptr())
+        return P[:, :self.num_visible]
+
+    def sample_class(self, hidden_activations):
+        L = _lib.load()
+        h = self._pad_rows(hidden_activations, self.num_hidden)
+        B = h.shape[0]
+        P = _padded(B, self.num_classes, self.device)
+        self._call(L.qbm_rbm_sample_class, self._U.data_ptr(), self.class_bias.data_ptr(), h.data_ptr(), B, self.num_hidden,
+                   self.num_classes, P.data_ptr())
+        return P[:, :self.num_classes]
+
+    def sample_class_given_x(self, input_data):
+        L = _lib.load()
+        x = self._pad_rows(input_data, self.num_visible)
+        B = x.shape[0]
+        P = _padded(B, self.num_classes, self.device)
+        ws = self._workspace(B)
+        self._call(L.qbm_rbm_class_given_x, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
+                   self.class_bias.data_ptr(), x.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes,
+                   P.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+        return P[:, :self.num_classes]
+
+    # ---- training steps -----------------------------------------------------------------------------------
+    def discriminative_training(self, input_data, class_label, factor=1):
+        """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors."""
+        L = _lib.load()
+        x = self._pad_rows(input_data, self.num_visible)
+        B = x.shape[0]
+        if B < 2:
+            raise ValueError("batch size must be >= 2 (the reference squeezes the batch axis at B = 1, :134)")
+        y = self._labels(class_label, B)
+        probs = _padded(B, self.num_classes, self.device)
+        pred = torch.empty(B, dtype=torch.int32, device=self.device)
+        loss = torch.empty(1, dtype=torch.float32, device=self.device)
+        ws = self._workspace(B)
+        self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
+                   self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), x.data_ptr(), y.data_ptr(), B, self.num_visible,
+                   self.num_hidden, self.num_classes, float(self.learning_rate), float(factor), float(self.sparse_constant),
+                   probs.data_ptr(), pred.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+        self._step += 1
+        return loss[0], pred.to(torch.int64), probs[:, :self.num_classes]
+
+    def cd1_training(self, input_data, class_label):
+        """One CD-1 step (k = 1) on a minibatch; parameters updated in place."""
+        L = _lib.load()
+        v0 = self._pad_rows(input_data, self.num_visible)
+        B = v0.shape[0]
+        y0 = self._labels(class_label, B)
+        ws = self._workspace(B)
+        self._call(L.qbm_rbm_cd1_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
+                   self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(), y0.data_ptr(), B, self.num_visible,
+                   self.num_hidden, self.num_classes, float(self.learning_rate), float(self.sparse_constant),
+                   ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(self._step & 0x3FFFFFFF),
+                   ws.data_ptr(), ws.numel() * 4)
+        self._step += 1
+
+    def predict(self, input_data):
+        return self.sample_class_given_x(input_data).argmax(dim=1)

@@ -1,0 +1,160 @@
+"""GPU: the tcgen05 TF32 GEMM and the ClassificationRBM path (boundary B3) against a plain PyTorch
+fp32 reference of the same op, the numpy oracle and the golden fixture from the reference's own class.
+Tolerances reflect TF32 operands (10-bit mantissa) with fp32 accumulation (north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle as M
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def tf32(x: torch.Tensor) -> torch.Tensor:
+    """Round-toward-zero to 10 mantissa bits (what the tensor core reads from fp32 operands)."""
+    return (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
+
+
+@pytest.mark.parametrize("M_,N,K", [(128, 128, 32), (256, 500, 784), (784, 500, 256), (100, 36, 64), (7, 12, 8),
+                                    (300, 129, 260), (1024, 1024, 512)])
+def test_gemm_tf32_vs_torch(qbm, cuda, M_, N, K):
+    g = torch.Generator(device="cpu").manual_seed(M_ + N + K)
+    A = torch.randn(M_, K, generator=g).to(cuda)
+    B = torch.randn(N, K, generator=g).to(cuda)
+    C, Ct = qbm.gemm_tf32(A, B, want_transposed=True)
+    ref32 = A.double() @ B.double().T
+    # exact model of the tensor core inputs: products of tf32-truncated operands, fp32 accumulation
+    ref_tf = (tf32(A).double() @ tf32(B).double().T)
+    err_model = (C.double() - ref_tf).abs().max().item()
+    scale = ref32.abs().max().item()
+    assert err_model <= 2e-5 * scale + 1e-4, f"differs from the tf32 model by {err_model}"
+    assert (C.double() - ref32).abs().max().item() <= 4e-3 * np.sqrt(K)          # tf32 tolerance vs fp32 math
+    assert torch.equal(Ct, C.T.contiguous())
+    # fused epilogue: bias + sigmoid, and SGD accumulate
+    bias = torch.randn(N, generator=g).to(cuda)
+    S = qbm.gemm_tf32(A, B, alpha=0.05, bias=bias, act=1)
+    assert torch.allclose(S, torch.sigmoid(0.05 * ref_tf.float() + bias), atol=2e-4)
+    C0 = torch.randn(M_, N, generator=g).to(cuda)
+    acc = qbm.gemm_tf32(A, B, alpha=-0.01, beta=1.0, Cin=C0)
+    assert torch.allclose(acc, C0 - 0.01 * ref_tf.float(), atol=1e-4 * max(1.0, scale * 0.01))
+
+
+def _model_from_golden(qbm, g):
+    m = qbm.B200ClassificationRBM(64, 32, k=1, num_classes=10, learning_rate=float(g["lr"]), seed=42)
+    m.weights = torch.from_numpy(g["W0"]); m.class_weights = torch.from_numpy(g["U0"])
+    m.visible_bias = torch.from_numpy(g["bv0"]).to(m.device); m.hidden_bias = torch.from_numpy(g["bh0"]).to(m.device)
+    m.class_bias = torch.from_numpy(g["bc0"]).to(m.device)
+    return m
+
+
+def test_rbm_initialisation_matches_reference(qbm, cuda):
+    """Same RNG protocol as ClassificationRBM.__init__ (:14-15, :26-30)."""
+    g = np.load(os.path.join(G, "rbm_discriminative.npz"))
+    m = qbm.B200ClassificationRBM(64, 32, k=1, num_classes=10, learning_rate=0.05, seed=42)
+    assert np.array_equal(m.weights.cpu().numpy(), g["W0"])
+    assert np.array_equal(m.visible_bias.cpu().numpy(), g["bv0"])
+    assert m.class_weights.shape == (10, 32) and float(m.class_weights.abs().sum()) == 0.0
+    assert m.weights.shape == (64, 32) and m.hidden_bias.shape == (32,) and m.class_bias.shape == (10,)
+
+
+def test_rbm_primitives_vs_golden(qbm, cuda):
+    g = np.load(os.path.join(G, "rbm_discriminative.npz"))
+    m = _model_from_golden(qbm, g)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    onehot = torch.nn.functional.one_hot(y[0], 10).float()
+    assert np.allclose(m.sample_hidden(x[0], onehot).cpu().numpy(), g["ph0"], atol=2e-3)
+    assert np.allclose(m.sample_visible(torch.from_numpy(g["hbin"])).cpu().numpy(), g["pv0"], atol=2e-3)
+    assert np.allclose(m.sample_class(torch.from_numpy(g["hbin"])).cpu().numpy(), g["pc0"], atol=1e-5)
+    assert np.allclose(m.sample_class_given_x(x[0]).cpu().numpy(), g["pyx0"], atol=3e-3)
+
+
+def test_rbm_discriminative_steps_vs_golden(qbm, cuda):
+    """R4/R5: two steps of discriminative_training against the reference's own class (torch CPU fp32)."""
+    g = np.load(os.path.join(G, "rbm_discriminative.npz"))
+    m = _model_from_golden(qbm, g)
+    x, y = torch.from_numpy(g["x"]), torch.from_numpy(g["y"])
+    for s in range(2):
+        err, pred, probs = m.discriminative_training(x[s], y[s])
+        assert probs.shape == (16, 10)
+        assert np.allclose(probs.cpu().numpy(), g[f"probs{s}"], atol=3e-3)
+        agree = np.mean(pred.cpu().numpy() == g[f"pred{s}"])
+        assert agree >= 0.9
+        assert abs(float(err) - float(g[f"err{s}"])) < 2e-3
+        assert np.allclose(m.weights.cpu().numpy(), g[f"W{s + 1}"], atol=2e-4)
+        assert np.allclose(m.class_weights.cpu().numpy(), g[f"U{s + 1}"], atol=2e-4)
+        assert np.allclose(m.hidden_bias.cpu().numpy(), g[f"bh{s + 1}"], atol=2e-4)
+        assert np.allclose(m.class_bias.cpu().numpy(), g[f"bc{s + 1}"], atol=2e-4)
+        assert np.array_equal(m.visible_bias.cpu().numpy(), g[f"bv{s + 1}"])
+        assert torch.equal(m._Wt[:, :64], m._W[:, :32].T)               # W^T kept in sync
+    with pytest.raises(ValueError):
+        m.discriminative_training(x[0][:1], y[0][:1])
+
+
+def synthetic_images(n, seed, V=784, C=10):
+    """binarised images, pixel-on probability 0.2 + 0.6 * template_c[pixel]."""
+    rng = np.random.default_rng(19)
+    templates = (rng.random((C, V)) < 0.5).astype(np.float32)
+    rng = np.random.default_rng(seed)
+    y = rng.integers(0, C, n)
+    x = (rng.random((n, V)) < 0.2 + 0.6 * templates[y]).astype(np.float32)
+    return x, y
+
+
+def test_rbm_training_accuracy_within_1pp_of_cpu_reference_math(qbm, cuda):
+    """Config C2 shapes (784 + 10 visible, 500 hidden, batch 256): a few discriminative steps on synthetic
+    images; test accuracy within 1 pp of the same steps done by the oracle in fp32 numpy."""
+    V, H, C, B = 784, 500, 10, 256
+    xtr, ytr = synthetic_images(1024, 1)
+    xte, yte = synthetic_images(512, 2)
+    m = qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=0.05, seed=42)
+    W, U = m.weights.cpu().numpy().copy(), m.class_weights.cpu().numpy().copy()
+    bv, bh, bc = m.visible_bias.cpu().numpy().copy(), m.hidden_bias.cpu().numpy().copy(), m.class_bias.cpu().numpy().copy()
+    for s in range(4):
+        xb, yb = xtr[s * B:(s + 1) * B], ytr[s * B:(s + 1) * B]
+        m.discriminative_training(torch.from_numpy(xb), torch.from_numpy(yb))
+        new, *_ = M.rbm_discriminative_step(W, U, bv, bh, bc, xb, yb, 0.05)
+        W, U, bv, bh, bc = (new[k].astype(np.float32) for k in ("W", "U", "b_v", "b_h", "b_c"))
+    acc_gpu = float((m.predict(torch.from_numpy(xte)).cpu().numpy() == yte).mean())
+    acc_ref = float((M.rbm_class_given_x(W, U, bh, bc, xte).argmax(axis=1) == yte).mean())
+    assert acc_ref > 0.5, "synthetic task should be learnable"
+    assert abs(acc_gpu - acc_ref) <= 0.01
+    assert np.allclose(m.weights.cpu().numpy(), W, atol=5e-4)
+
+
+def test_rbm_cd1_step_statistics(qbm, cuda):
+    """CD-1 composition: the update equals lr/B * (v0^T ph0 - v1^T ph1) for SOME valid Bernoulli draws: check
+    the deterministic parts exactly (positive phase) and the sampled parts statistically."""
+    V, H, C, B = 784, 500, 10, 256
+    x, y = synthetic_images(B, 3)
+    m = qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=0.1, seed=7)
+    m.class_weights = torch.randn(C, H) * 0.05
+    W0 = m.weights.clone(); U0 = m.class_weights.clone()
+    bv0, bh0, bc0 = m.visible_bias.clone(), m.hidden_bias.clone(), m.class_bias.clone()
+    xt, yt = torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda)
+    onehot = torch.nn.functional.one_hot(yt, C).float()
+    ph0 = torch.sigmoid(xt @ W0 + bh0 + onehot @ U0)
+    m.cd1_training(xt, yt)
+    dW = (m.weights - W0) * B / 0.1                       # = v0^T ph0 - v1^T ph1
+    dbv = (m.visible_bias - bv0) * B / 0.1                # = sum(v0 - v1)
+    dbh = (m.hidden_bias - bh0) * B / 0.1                 # = sum(ph0 - ph1)
+    # expectation of the negative phase under the model (mean-field estimate): v1 ~ sigmoid(h0 W^T + b_v)
+    pv1 = torch.sigmoid(ph0 @ W0.T + bv0)
+    assert torch.isfinite(m.weights).all()
+    # visible bias gradient: sum(v0) - sum(v1), v1 Bernoulli with mean ~ pv1 (loose 6-sigma band per pixel)
+    exp_dbv = xt.sum(0) - pv1.sum(0)
+    sd = torch.sqrt((pv1 * (1 - pv1)).sum(0) + 1.0)
+    assert ((dbv - exp_dbv).abs() <= 6 * sd + 25).float().mean() > 0.98
+    # hidden bias: ph1 is a probability, so |dbh| <= B and sign structure follows ph0 - ph1
+    assert dbh.abs().max() <= B + 1e-3
+    # weights: positive part must be present: dW + v1^T ph1 = v0^T ph0  =>  dW <= v0^T ph0 elementwise (+ tf32 slack)
+    pos = xt.T @ ph0
+    assert (dW <= pos + 0.5).all() and (dW >= pos - B - 0.5).all()
+    assert torch.equal(m._Wt[:, :V], m._W[:, :H].T)
+    # reproducible: same seed, same step -> same update
+    m2 = qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=0.1, seed=7)
+    m2.class_weights = U0
+    m2.cd1_training(xt, yt)
+    assert torch.equal(m2.weights, m.weights) and torch.equal(m2.class_bias, m.class_bias)
