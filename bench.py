@@ -235,6 +235,31 @@ def run_gpu(args):
     h2d = J.astype(np.float32).nbytes + h.astype(np.float32).nbytes + betas.astype(np.float32).nbytes + Q.nbytes
     d2h = smp.nbytes + en.nbytes
 
+    # ---- training legs: QBM train images/s (configs 1, 3, 5) and the ClassificationRBM steps (config 2)
+    train = None
+    if not args.no_train:
+        import bench_train as BT
+        train = {}
+        pg = dist.group.WORLD if distributed else None
+        legs = [("c1", "disc"), ("c3", "disc"), ("c5", "disc"), ("c2", "disc"), ("c2", "cd1")]
+        for cfg, mode in legs:
+            batch = BT.CONFIGS[cfg][1]
+            tms, te2e, th2d = BT.gpu_train_rate(cfg, qbm_b200, torch, dev, world, rank, barrier, batch, args.train_steps,
+                                                3, pg=pg, mode=mode)
+            if distributed:
+                tt = torch.tensor([tms, te2e], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                tms, te2e = float(tt[0]), float(tt[1])
+            # C2 has no cross-rank exchange in this round: N independent replicas
+            imgs = float(world) * args.train_steps * batch
+            key = cfg if cfg != "c2" else f"c2_{mode}"
+            train[key] = {"workload": BT.CONFIGS[cfg][0] + (f" [{mode} step]" if cfg == "c2" else ""),
+                          "metric": "train images/sec", "value": imgs / (tms * 1e-3), "unit": "images/s",
+                          "batch_per_gpu": batch, "steps": args.train_steps, "ms_per_step": tms / args.train_steps,
+                          "scaling": "weak" if cfg != "c2" else "replicas only",
+                          "e2e": {"value": imgs / te2e, "unit": "images/s", "h2d_bytes_per_step": th2d,
+                                  "d2h_bytes_per_step": 8}}
+
     if distributed:
         t = torch.tensor([ms, e2e_s, float(acc), float(prop), sa_ms], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -294,6 +319,17 @@ def run_gpu(args):
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{cores} threads x {rpt} reads x {NUM_SWEEPS} sweeps at n={n} ({dt:.1f} s); "
                              "oracle/neal_sa.c = dwave-neal 0.5.9 cpu_sa.cpp restated (float64, xorshift128+)"}
+        if train is not None and world == 1 and not args.no_cpu_baseline:
+            import bench_train as BT
+            for cfg, images in (("c1", 2 * cores), ("c3", cores), ("c5", cores)):
+                rate, dt = BT.cpu_train_rate(cfg, images, cores)
+                train[cfg]["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                                              "sample": f"{images} images, one per thread, both phases through "
+                                                        f"oracle/neal_sa.c + oracle/model_oracle.py ({dt:.1f} s)"}
+            for mode in ("disc", "cd1"):
+                rate, dt = BT.cpu_rbm_rate(8, 256, mode)
+                train[f"c2_{mode}"]["cpu_baseline"] = {"value": rate, "unit": "images/s", "cores": cores, "kind": "port",
+                                                       "sample": f"8 steps of batch 256, float32 numpy ({dt:.1f} s)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -310,6 +346,7 @@ def run_gpu(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clk,
+            "train": train,
         }
         print(json.dumps(line), flush=True)
     if distributed:
@@ -324,6 +361,8 @@ def main():
     ap.add_argument("--reads", type=int, default=9472, help="reads per GPU per step (default 148 SMs x 16 chains x 4 waves)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the QBM / RBM training-throughput legs")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed minibatches per training leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -154,6 +154,22 @@ int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, floa
                      void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K6  Conv-Deep inference context for a minibatch: valid convolution with the shared kernel,
+ * deterministic p x p pooling (argmin per window) and the input patch of every active unit.
+ * ref: src/model/geometry.py:37-53 (conv2d_valid_stride), src/model/layers.py:65-84
+ *      (pooled_indices_for_input), src/train/train.py:188-191 (patch gather), reached through
+ *      src/model/inference.py:16-44 (prepare_context).
+ *   X [B, ih, iw] float64, kernel [k, k] float64 (k*k <= 128)
+ *   fmap_out    [B, oh*ow] float64, bit-identical to the reference (numpy's pairwise order)
+ *   pooled_out  [B, P] int32 index into the flattened feature map, P = qbm_convdeep_num_pooled(...)
+ *               (pool in {0,1}: every conv unit is active, P = oh*ow)
+ *   patches_out [B, P, k, k] float64 (nullable)
+ */
+int qbm_convdeep_num_pooled(int ih, int iw, int k, int stride, int pool);
+int qbm_convdeep_context(const double *X, const double *kernel, long long B, int ih, int iw, int k, int stride,
+                         int pool, double *fmap_out, int *pooled_out, double *patches_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that
  * tests can compare them bit-for-bit with the oracle's independent C restatement.
  *   qbm_test_philox: ctr [count,4] u32, key [count,2] u32 -> out [count,4] u32

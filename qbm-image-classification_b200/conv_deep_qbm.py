@@ -1,0 +1,297 @@
+"""Batched, device-resident training step of the Conv-Deep QBM (the model ``cdqbm_main.py`` runs).
+
+Mirrors ``Conv_Deep_QBM`` (src/model/cdqbm_state.py:13-215) and the functions that drive it --
+``prepare_context`` (src/model/inference.py:16-44), ``build_unclamped_qubo`` / ``build_clamped_qubo``
+(src/qubo/builder.py:21-110), ``run_unclamped`` / ``run_clamped`` (src/train/pipeline.py:13-36),
+``train_one_iteration`` and ``get_average_configuration_single`` (src/train/train.py:12-253): same
+constructor arguments, same parameter attribute names, shapes and initial draws, same variable layout
+``[pooled conv | sequential layers | outputs]``, same learning rule.  What changes is the execution --
+the reference's per-image loop (context, two QUBOs, two ``sampler.sample_Q`` calls, two statistics
+passes per image) becomes one pass over the minibatch:
+
+    X --K6--> feature maps, pooled units, patches --> 2B QUBOs --K0--> spin models --K1--> chains
+      --K3--> moments --> parameter-shaped statistics --[all-reduce over ranks]--> SGD update
+
+Supported configuration = what runs in the reference: deterministic pooling
+(``pooling_size`` >= 2 or no pooling), ``hidden_bias_type`` "shared" or "none".  Probabilistic pooling
+and per-unit conv biases crash inside the reference and are rejected here.
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+import torch
+
+from . import _lib, ising, sampler as _s
+from .disc_qbm import schedule_device
+
+
+class ConvDeepQBM:
+    def __init__(self, num_visible_nodes, num_lable_nodes, image_shape=(28, 28), seed=77, kernel_size=3, pooling_size=0,
+                 pooling_type="deterministic", stride=1, sequential_layer_sizes=None, param_string="", load_path="",
+                 speicherort=None, is_restricted=False, hidden_bias_type="none", solver="SA", anneal=1000, token="",
+                 initial_states_generator="numpy", shared_stream=True, stats_dtype="float32", device=None,
+                 process_group=None):
+        if str(solver).upper() != "SA":
+            raise ValueError("the B200 path implements solver='SA' only (the D-Wave adapter is out of scope)")
+        if pooling_type != "deterministic":
+            raise ValueError("only deterministic pooling is supported (probabilistic pooling raises inside the "
+                             "reference's statistics, src/train/train.py:189)")
+        if hidden_bias_type not in ("shared", "none"):
+            raise ValueError("hidden_bias_type must be 'shared' or 'none' (per-unit conv biases need "
+                             "model.pooled_units, which the reference never sets, src/train/train.py:176)")
+        if stats_dtype not in ("float32", "float64"):
+            raise ValueError("stats_dtype must be 'float32' (the reference's sample dtype) or 'float64'")
+        self.kernel_size, self.pooling_size, self.pooling_type = int(kernel_size), int(pooling_size), pooling_type
+        self.stride, self.image_shape = int(stride), tuple(int(v) for v in image_shape)
+        self.sequential_layer_sizes = [int(s) for s in (sequential_layer_sizes or [])]
+        self.num_visible, self.num_lable_nodes = num_visible_nodes, int(num_lable_nodes)
+        self.seed, self.is_restricted, self.hidden_bias_type = seed, bool(is_restricted), hidden_bias_type
+        self.param_string, self.load_path, self.speicherort = param_string, load_path, speicherort
+        self.anneal = int(anneal)
+        self.initial_states_generator, self.shared_stream, self.stats_dtype = initial_states_generator, shared_stream, stats_dtype
+        self.device = _s._require_cuda(device)
+        self.pg = process_group
+        # ---- geometry (cdqbm_state.py:99-136, geometry.py:7-18,56-100) ----
+        ih, iw = self.image_shape
+        k, s = self.kernel_size, self.stride
+        self.conv_layer_dim = ((ih - k) // s + 1, (iw - k) // s + 1)
+        self.num_conv_units = self.conv_layer_dim[0] * self.conv_layer_dim[1]
+        P = _lib.load().qbm_convdeep_num_pooled(ih, iw, k, s, self.pooling_size)
+        if P < 1:
+            raise ValueError(f"bad geometry: image {self.image_shape}, kernel {k}, stride {s}, pooling {pooling_size}")
+        self.num_pooled_units = P
+        self.num_hidden_units_per_layer = [self.num_conv_units] + self.sequential_layer_sizes
+        self.num_active_units_per_layer = [self.num_conv_units, P] + self.sequential_layer_sizes
+        self.num_active_units = sum(self.num_active_units_per_layer)
+        self.num_hidden_nodes = self.num_conv_units + sum(self.sequential_layer_sizes)
+        self.n_hidden = P + sum(self.sequential_layer_sizes)          # QUBO variables besides the outputs
+        # ---- parameters: same draws in the same order as cdqbm_state.py:143-215 (MODEL.__init__ seeds first) ----
+        np.random.seed(seed)
+        random.seed(seed)
+        np.random.seed(seed)
+        nl = self.num_lable_nodes
+        kernel = np.random.uniform(-1, 1, (k, k))
+        W_seq = [np.random.uniform(-1, 1, (self.num_active_units_per_layer[1 + i], n))
+                 for i, n in enumerate(self.sequential_layer_sizes)]
+        # np.triu of a 1-D draw: a size x size matrix whose rows repeat the vector (Appendix B Q10)
+        W_intra = None if self.is_restricted else [np.triu(np.random.uniform(-1, 1, n)) for n in self.sequential_layer_sizes]
+        W_hy = np.random.uniform(-1, 1, (self.num_active_units_per_layer[-1], nl))
+        W_oo = np.triu(np.random.uniform(-1, 1, (nl, nl)), k=1)
+        if hidden_bias_type == "shared":
+            b_conv = np.random.uniform(-1, 1, 1)
+        else:
+            b_conv = np.zeros(self.sequential_layer_sizes)             # the reference's placeholder (:178), never used
+        b_seq = np.random.uniform(-1, 1, sum(self.sequential_layer_sizes))
+        b_out = np.random.uniform(-1, 1, nl)
+        self._p = {}
+        self.set_params(kernel=kernel, W_seq=W_seq, W_intra=W_intra, W_hy=W_hy, W_oo=W_oo, b_conv=b_conv, b_seq=b_seq,
+                        b_out=b_out)
+        self._init_cache = {}
+        self.keep_samples = False
+        self.last_samples = None
+        self.step_count = 0
+
+    # ---- parameters: device tensors, exposed under the reference's attribute names -------------
+    _NAMES = {"kernel_weights": "kernel", "weights_sequential_layer": "W_seq", "weights_hidden_to_output": "W_hy",
+              "weights_output_output": "W_oo", "weights_interlayer_sequential": "W_intra", "biases_conv_units": "b_conv",
+              "biases_sequential_units": "b_seq", "biases_output": "b_out"}
+
+    def _dev(self, v):
+        return torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device).clone()
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if v is None:
+                self._p[k] = None
+            elif isinstance(v, (list, tuple)):
+                self._p[k] = [self._dev(a) for a in v]
+            else:
+                self._p[k] = self._dev(v)
+
+    def get_params(self) -> dict:
+        out = {}
+        for k, v in self._p.items():
+            out[k] = None if v is None else ([a.cpu().numpy() for a in v] if isinstance(v, list) else v.cpu().numpy())
+        return out
+
+    def __getattr__(self, name):
+        names = type(self)._NAMES
+        if name in names and "_p" in self.__dict__:
+            return self.get_params()[names[name]]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in type(self)._NAMES and "_p" in self.__dict__:
+            self.set_params(**{type(self)._NAMES[name]: value})
+        else:
+            object.__setattr__(self, name, value)
+
+    @property
+    def weight_objects(self):
+        p = self.get_params()
+        return [p["kernel"], p["W_seq"], p["W_hy"], p["W_oo"], p["W_intra"], p["b_conv"], p["b_seq"], p["b_out"]]
+
+    # ---- context (inference.py:16-44) ---------------------------------------------------------------
+    def prepare_context_batch(self, X):
+        """(fmap f64 [B, oh*ow], pooled_idx int32 [B, P], patches f64 [B, P, k, k]) for images [B, ih, iw] (K6)."""
+        Xd = torch.as_tensor(np.asarray(X) if not torch.is_tensor(X) else X).to(self.device, torch.float64).contiguous()
+        if Xd.dim() == 2:
+            Xd = Xd[None]
+        B, ih, iw = Xd.shape
+        if (ih, iw) != self.image_shape:
+            raise ValueError(f"images are {ih}x{iw}, the model was built for {self.image_shape}")
+        k, P = self.kernel_size, self.num_pooled_units
+        fmap = torch.empty((B, self.num_conv_units), dtype=torch.float64, device=self.device)
+        pooled = torch.empty((B, P), dtype=torch.int32, device=self.device)
+        patches = torch.empty((B, P, k, k), dtype=torch.float64, device=self.device)
+        L = _lib.load()
+        with torch.cuda.device(self.device):
+            rc = L.qbm_convdeep_context(Xd.data_ptr(), self._p["kernel"].data_ptr(), B, ih, iw, k, self.stride,
+                                        self.pooling_size, fmap.data_ptr(), pooled.data_ptr(), patches.data_ptr(),
+                                        _s._stream_ptr(self.device))
+        _lib.check(rc)
+        return fmap, pooled, patches
+
+    # ---- QUBO construction (builder.py:21-110) -------------------------------------------------------
+    def _blocks(self):
+        P, sizes = self.num_pooled_units, self.sequential_layer_sizes
+        starts = [0, P]
+        for s in sizes:
+            starts.append(starts[-1] + s)
+        layers = [(starts[i], starts[i + 1]) for i in range(len(sizes) + 1)]     # [pooled, seq_1, ..., seq_k]
+        return layers, layers[-1]
+
+    def build_qubos(self, fmap: torch.Tensor, pooled: torch.Tensor, Y: torch.Tensor | None, beta_eff: float = 1.0):
+        """float64 [B, n, n]: n = n_hidden (+ num_lable_nodes when ``Y`` is None, i.e. unclamped)."""
+        p, P, nh, nl = self._p, self.num_pooled_units, self.n_hidden, self.num_lable_nodes
+        B = fmap.shape[0]
+        n = nh + (nl if Y is None else 0)
+        layers, last = self._blocks()
+        upper = torch.zeros((n, n), dtype=torch.float64, device=self.device)
+        for li, W in enumerate(p["W_seq"]):
+            (ps, pe), (cs, ce) = layers[li], layers[li + 1]
+            upper[ps:pe, cs:ce] += W
+            if p["W_intra"] is not None:
+                upper[cs:ce, cs:ce] += torch.triu(p["W_intra"][li], diagonal=1)
+        diag = torch.zeros((B, n), dtype=torch.float64, device=self.device)
+        conv = fmap.gather(1, pooled.to(torch.int64))
+        if self.hidden_bias_type == "shared":
+            conv = conv + p["b_conv"][0]
+        diag[:, :P] = conv
+        if p["b_seq"].numel():
+            diag[:, P:nh] += p["b_seq"][None, :]
+        if Y is None:
+            upper[last[0]:last[1], nh:] += p["W_hy"]
+            upper[nh:, nh:] += torch.triu(p["W_oo"], diagonal=1)
+            diag[:, nh:] += p["b_out"][None, :]
+        else:
+            diag[:, last[0]:last[1]] += Y @ p["W_hy"].T                       # label bias (:106-108)
+        return ((torch.diag_embed(diag) + upper[None]) / float(beta_eff)).contiguous()
+
+    # ---- sampling (pipeline.py:20,35 -> sampler.py:26-33) -----------------------------------------------
+    def _init_states(self, B, n, num_reads):
+        if self.initial_states_generator == "philox":
+            return None
+        key = (num_reads, n)
+        if key not in self._init_cache:              # LocalSASampler passes the same seed on every call (Q6)
+            self._init_cache[key] = torch.from_numpy(ising.initial_states_numpy(self.seed, num_reads, n)).to(self.device)
+        return self._init_cache[key][None].expand(B, -1, -1).contiguous()
+
+    def sample_batch(self, Q: torch.Tensor, num_reads: int, first_image: int = 0) -> torch.Tensor:
+        B, n, _ = Q.shape
+        J, hh, _, rng = _s.qubo_to_ising_device(Q)
+        betas, spb = schedule_device(rng, self.anneal)
+        flags = 2 if self.shared_stream else 0
+        off = 0 if self.shared_stream else first_image * int(num_reads)
+        return _s.sa_sample(J, hh, betas, spb, int(num_reads), self.seed, chain_offset=off,
+                            init_states=self._init_states(B, n, int(num_reads)), flags=flags).states
+
+    # ---- class probabilities (pipeline.py:22-28) ------------------------------------------------------
+    def _probs(self, mean_u: torch.Tensor, one_hot: bool) -> torch.Tensor:
+        out = mean_u[:, self.n_hidden:].to(torch.float32)
+        if not one_hot:
+            p1 = out[:, 0].to(torch.float64).clamp(1e-12, 1 - 1e-12)
+            return torch.stack((1.0 - p1, p1), dim=1).to(torch.float32)
+        s = out.sum(dim=1, keepdim=True)
+        uni = torch.full_like(out, 1.0 / out.shape[1])
+        return torch.where(s > 0, out / torch.where(s > 0, s, torch.ones_like(s)), uni)
+
+    def _moments(self, S: torch.Tensor, second: bool = True):
+        mean, sec = _s.phase_stats(S, second=second)
+        if self.stats_dtype == "float32":           # the reference averages float32 samples (sampler.py:33)
+            mean = mean.to(torch.float32).to(torch.float64)
+            sec = None if sec is None else sec.to(torch.float32).to(torch.float64)
+        return mean, sec
+
+    # ---- statistics -> parameter-shaped errors, summed over the local images (train.py:135-253) ------
+    def _errors(self, patches, Ylab, mc, sc, mu, su) -> dict:
+        P, nh, nl = self.num_pooled_units, self.n_hidden, self.num_lable_nodes
+        layers, last = self._blocks()
+        e = {}
+        if self.hidden_bias_type == "shared":
+            e["b_conv"] = (mc[:, :P].sum(dim=1) - mu[:, :P].sum(dim=1)).sum().reshape(1)
+        e["b_seq"] = (mc[:, P:nh] - mu[:, P:nh]).sum(dim=0)
+        e["b_out"] = (Ylab - mu[:, nh:]).sum(dim=0)
+        e["kernel"] = torch.einsum("bpij,bp->ij", patches, mc[:, :P] - mu[:, :P])
+        e["W_seq"], e["W_intra"] = [], []
+        for li in range(len(self.sequential_layer_sizes)):
+            (ps, pe), (cs, ce) = layers[li], layers[li + 1]
+            e["W_seq"].append((sc[:, ps:pe, cs:ce] - su[:, ps:pe, cs:ce]).sum(dim=0))
+            if not self.is_restricted:
+                e["W_intra"].append(torch.triu((sc[:, cs:ce, cs:ce] - su[:, cs:ce, cs:ce]).sum(dim=0), diagonal=1))
+        ls, le = last
+        e["W_hy"] = mc[:, ls:le].T @ Ylab - su[:, ls:le, nh:].sum(dim=0)
+        e["W_oo"] = torch.triu(Ylab.T @ Ylab - su[:, nh:, nh:].sum(dim=0), diagonal=1)
+        return e
+
+    def _labels(self, Y, B, one_hot):
+        y = (Y if torch.is_tensor(Y) else torch.as_tensor(np.asarray(Y))).to(self.device).reshape(B).to(torch.int64)
+        if one_hot:
+            return y, torch.nn.functional.one_hot(y, self.num_lable_nodes).to(torch.float64)
+        return y, y.to(torch.float64)[:, None]
+
+    def train_one_iteration(self, X, Y, num_reads: int, beta_eff: float, lr: float, one_hot: bool = False,
+                            global_batch=None, first_image: int = 0) -> float:
+        """src/train/train.py:12-132 for a whole minibatch; returns the mean loss.  With a process group,
+        ``X`` is this rank's shard, ``global_batch`` the minibatch size and ``first_image`` the shard's offset."""
+        fmap, pooled, patches = self.prepare_context_batch(X)
+        B = fmap.shape[0]
+        y, Ylab = self._labels(Y, B, one_hot)
+        Sc = self.sample_batch(self.build_qubos(fmap, pooled, Ylab, beta_eff), num_reads, first_image)
+        Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads, first_image)
+        mc, sc = self._moments(Sc)
+        mu, su = self._moments(Su)
+        if self.keep_samples:
+            self.last_samples = (Sc, Su)
+        probs = self._probs(mu, one_hot)
+        py = probs.gather(1, y[:, None])[:, 0].to(torch.float64)
+        loss_sum = -torch.log(torch.clamp(py, min=1e-12)).sum()
+        err = self._errors(patches, Ylab, mc, sc, mu, su)
+        names = [k for k in ("b_conv", "b_seq", "b_out", "kernel", "W_seq", "W_intra", "W_hy", "W_oo")
+                 if k in err and not (k == "W_intra" and self.is_restricted)]
+        parts = []
+        for k in names:
+            parts += [t.reshape(-1) for t in (err[k] if isinstance(err[k], list) else [err[k]])]
+        flat = torch.cat(parts + [loss_sum.reshape(1)])
+        if self.pg is not None:
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        gb = float(global_batch if global_batch is not None else B)
+        pos = 0
+        for k in names:
+            tgt = self._p[k] if isinstance(self._p[k], list) else [self._p[k]]
+            for t in tgt:
+                cnt = t.numel()
+                t -= lr * (flat[pos:pos + cnt].reshape(t.shape) / gb)
+                pos += cnt
+        self.step_count += 1
+        return float(flat[-1].item() / max(1.0, gb))
+
+    # ---- prediction (cdqbm_main.py:119-127 -> run_unclamped) --------------------------------------------
+    def predict_proba_batch(self, X, num_reads: int, beta_eff: float = 1.0, one_hot: bool = False) -> np.ndarray:
+        fmap, pooled, _ = self.prepare_context_batch(X)
+        Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads)
+        mu, _ = self._moments(Su, second=False)
+        return self._probs(mu, one_hot).cpu().numpy()

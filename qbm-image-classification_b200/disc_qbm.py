@@ -132,9 +132,14 @@ class DiscQBM:
         return [p["W_vh"], p["W_vo"], p["b_h"], p["b_o"], p["W_oo"], p["W_hh"]]
 
     # ---- QUBO construction (faster_dqbm.py:225-284) ------------------------------------------------
+    def _to_dev(self, a) -> torch.Tensor:
+        """float64 device tensor from a numpy array (host -> device copy) or a tensor already on the device."""
+        if torch.is_tensor(a):
+            return a.to(self.device, torch.float64)
+        return torch.as_tensor(np.asarray(a, dtype=np.float64)).to(self.device)
+
     def _labels(self, y_batch, B):
-        Y = torch.as_tensor(np.asarray(y_batch, dtype=np.float64)).to(self.device)
-        return Y.reshape(B, self.n_output_nodes)
+        return self._to_dev(y_batch).reshape(B, self.n_output_nodes)
 
     def build_qubos(self, X: torch.Tensor, Y: torch.Tensor | None) -> torch.Tensor:
         """Batched ``create_qubo_matrix_from``: float64 [B, n, n] on the device."""
@@ -213,7 +218,7 @@ class DiscQBM:
         """faster_dqbm.py:998-1064 / discriminative_qbm.py:875-951 for a whole minibatch.  With a
         process group, ``x_batch`` is this rank's shard, ``global_batch`` the minibatch size the errors
         are divided by and ``first_image`` the shard's offset.  Returns (errors_biases_output, avg loss)."""
-        X = torch.as_tensor(np.asarray(x_batch, dtype=np.float64)).to(self.device)
+        X = self._to_dev(x_batch)
         B = X.shape[0]
         Y = self._labels(y_batch, B)
         Sc = self.sample_batch(self.build_qubos(X, Y), first_image)
@@ -251,7 +256,7 @@ class DiscQBM:
 
     # ---- prediction (faster_dqbm.py:1227-1241) ------------------------------------------------------
     def predict_batch(self, X) -> np.ndarray:
-        Xd = torch.as_tensor(np.asarray(X, dtype=np.float64)).to(self.device)
+        Xd = self._to_dev(X)
         Su = self.sample_batch(self.build_qubos(Xd, None))
         mean_u, _ = _s.phase_stats(Su, second=False)
         avg = mean_u[:, :self.n_output_nodes].cpu().numpy()
