@@ -173,10 +173,10 @@ int qbm_convdeep_context(const double *X, const double *kernel, long long B, int
  * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that
  * tests can compare them bit-for-bit with the oracle's independent C restatement.
  *   qbm_test_philox: ctr [count,4] u32, key [count,2] u32 -> out [count,4] u32
- *   qbm_test_exp:    x [count] f32 -> out [count] f32 (exp_spec of DESIGN.md section 3)
+ *   qbm_test_neg_log: u [count] u32 -> out [count] f32 (neg_log_u32 of DESIGN.md section 3)
  */
 int qbm_test_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out, long long count, void *stream);
-int qbm_test_exp(const float *x, float *out, long long count, void *stream);
+int qbm_test_neg_log(const uint32_t *u, float *out, long long count, void *stream);
 
 #ifdef __cplusplus
 }

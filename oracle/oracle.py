@@ -58,8 +58,8 @@ def lib() -> ctypes.CDLL:
         L.oracle_replay_sa.restype = c_i
         L.oracle_philox4x32_10.argtypes = [c_p, c_p, c_p]
         L.oracle_philox4x32_10.restype = None
-        L.oracle_exp_spec.argtypes = [ctypes.c_float]
-        L.oracle_exp_spec.restype = ctypes.c_float
+        L.oracle_neg_log_u32.argtypes = [ctypes.c_uint32]
+        L.oracle_neg_log_u32.restype = ctypes.c_float
         L.oracle_qubo_energy.argtypes = [c_i, c_p, ctypes.c_longlong, c_p, c_p]
         L.oracle_qubo_energy.restype = c_i
         _LIB = L
@@ -211,8 +211,8 @@ def philox4x32_10(ctr, key) -> np.ndarray:
     return o
 
 
-def exp_spec(x: float) -> float:
-    return float(lib().oracle_exp_spec(ctypes.c_float(x)))
+def neg_log_u32(u: int) -> float:
+    return float(lib().oracle_neg_log_u32(ctypes.c_uint32(int(u))))
 
 
 def qubo_energies(Q: np.ndarray, X01: np.ndarray) -> np.ndarray:

@@ -4,7 +4,7 @@
  * The REPLAY oracle: a plain sequential CPU restatement of the reference's Metropolis rule
  * (dwave-neal 0.5.9 cpu_sa.cpp as pinned in SURVEY.md Appendix A.5: fixed sweep order
  * v = 0..n-1, skip when dE >= 44.36142/beta, accept when dE <= 0, otherwise accept iff
- * exp(-dE*beta) > uniform) evaluated in the arithmetic of the sm_100a kernel and fed the
+ * exp(-dE*beta) > uniform, evaluated in the log domain) evaluated in the arithmetic of the sm_100a kernel and fed the
  * kernel's own counter-based Philox4x32-10 stream (BASELINE.json north_star: "SA trajectories
  * are bit-exact against a CPU replay of the reference's Metropolis rule fed the kernel's own
  * Philox stream").  It is written independently of csrc/ (no shared headers) from the
@@ -18,7 +18,8 @@
  *   proposal   dE = (s_v > 0 ? -2 : 2) * F_v
  *              dE >= thr -> skip ; dE <= 0 -> flip ;
  *              else u = philox(ctr = (chain_lo, chain_hi, t, ((v>>7)<<5)|(v&31)))[(v>>5)&3],
- *                   p = exp_spec(-(dE*beta)),  flip iff (uint64)(p * 2^32) > u
+ *                   flip iff dE < fminf(thr, neg_log_u32(u) / beta)
+ *              (the test u/2^32 < exp(-beta dE) in the log domain: dE < -ln(u/2^32) / beta)
  *   flip       c = (s_v > 0 ? -2 : 2) ; for all j : F_j = fmaf(c, J[v][j], F_j) ; s_v = -s_v
  *
  * Everything is IEEE binary32 with round-to-nearest-even; build with -ffp-contract=off so the
@@ -48,27 +49,37 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* ---- exp_spec: FMA-only exp for x in (-88, 0] -------------------------------------------- */
-float oracle_exp_spec(float x)
+/* ---- neg_log_u32: FMA-only -ln(u / 2^32) for a 32-bit uniform (u = 0 -> +inf) ------------------ */
+float oracle_neg_log_u32(uint32_t u)
 {
-    const float t = x * 1.44269504f;                 /* fp32 multiply */
-    const float k = rintf(t);                        /* round-half-even */
-    float f = fmaf(k, -0.693145751953125f, x);       /* ln2 high part (exact product) */
-    f = fmaf(k, -1.42860677e-06f, f);                /* ln2 low part */
-    float p = 1.9875691500e-4f;
-    p = fmaf(p, f, 1.3981999507e-3f);
-    p = fmaf(p, f, 8.3334519073e-3f);
-    p = fmaf(p, f, 4.1665795894e-2f);
-    p = fmaf(p, f, 1.6666665459e-1f);
-    p = fmaf(p, f, 5.0000001201e-1f);
-    const float f2 = f * f;
-    float r = fmaf(p, f2, f);
-    r = r + 1.0f;
+    if (u == 0u) return INFINITY;
+    const float x = (float)u;                        /* [1, 2^32], round to nearest even */
     int32_t bits;
-    memcpy(&bits, &r, sizeof bits);
-    bits += ((int32_t)k) << 23;                      /* scale by 2^k: result stays normal for x > -87 */
-    memcpy(&r, &bits, sizeof bits);
-    return r;
+    memcpy(&bits, &x, sizeof bits);
+    int e = (bits >> 23) - 127;
+    int32_t mb = (bits & 0x007fffff) | 0x3f800000;
+    float m;
+    memcpy(&m, &mb, sizeof m);                       /* [1, 2) */
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    const float f = m - 1.0f;                        /* exact */
+    const float z = f * f;
+    float y = 7.0376836292e-2f;                      /* Cephes logf polynomial on [sqrt(1/2)-1, sqrt(2)-1] */
+    y = fmaf(y, f, -1.1514610310e-1f);
+    y = fmaf(y, f, 1.1676998740e-1f);
+    y = fmaf(y, f, -1.2420140846e-1f);
+    y = fmaf(y, f, 1.4249322787e-1f);
+    y = fmaf(y, f, -1.6668057665e-1f);
+    y = fmaf(y, f, 2.0000714765e-1f);
+    y = fmaf(y, f, -2.4999993993e-1f);
+    y = fmaf(y, f, 3.3333331174e-1f);
+    y = y * f;
+    y = y * z;
+    y = fmaf(-0.5f, z, y);
+    const float r = f + y;                           /* ln(m) */
+    const float E = (float)(32 - e);
+    float nl = fmaf(E, 0.693359375f, -r);            /* ln2 high part */
+    nl = fmaf(E, -2.12194440e-4f, nl);               /* ln2 low part */
+    return nl;
 }
 
 static inline int philox_init_spin(uint64_t seed, uint64_t chain, int v)
@@ -123,10 +134,8 @@ int oracle_replay_sa(int n, int ld, const float *J, const float *h, int num_beta
                         uint32_t o[4];
                         oracle_philox4x32_10(ctr, key, o);
                         ++n_draw;
-                        const float x = -(dE * beta);
-                        const float p = oracle_exp_spec(x);
-                        const uint64_t pf = (uint64_t)(p * 4294967296.0f);
-                        flip = pf > (uint64_t)o[(v >> 5) & 3];
+                        const float bound = fminf(thr, oracle_neg_log_u32(o[(v >> 5) & 3]) / beta);
+                        flip = dE < bound;
                     }
                     if (flip) {
                         const float cf = (s[v] > 0 ? -2.0f : 2.0f);

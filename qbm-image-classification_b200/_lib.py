@@ -48,7 +48,7 @@ SIGNATURES = {
     "qbm_convdeep_num_pooled": (_c_i, [_c_i] * 5),
     "qbm_convdeep_context": (_c_i, [_c_p, _c_p, _c_ll, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p]),
     "qbm_test_philox": (_c_i, [_c_p, _c_p, _c_p, _c_ll, _c_p]),
-    "qbm_test_exp": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
+    "qbm_test_neg_log": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
 }
 
 _lib = None

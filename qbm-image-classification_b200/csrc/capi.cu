@@ -34,10 +34,10 @@ __global__ void test_philox_kernel(const uint32_t *ctr, const uint32_t *key, uin
     const Philox4 o = philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1]);
     out[4 * i] = o.x; out[4 * i + 1] = o.y; out[4 * i + 2] = o.z; out[4 * i + 3] = o.w;
 }
-__global__ void test_exp_kernel(const float *x, float *out, long long count)
+__global__ void test_neg_log_kernel(const uint32_t *u, float *out, long long count)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count) out[i] = exp_spec(x[i]);
+    if (i < count) out[i] = neg_log_u32(u[i]);
 }
 }  // namespace
 
@@ -50,11 +50,11 @@ extern "C" QBM_API int qbm_test_philox(const uint32_t *ctr, const uint32_t *key,
     return QBM_OK;
 }
 
-extern "C" QBM_API int qbm_test_exp(const float *x, float *out, long long count, void *stream)
+extern "C" QBM_API int qbm_test_neg_log(const uint32_t *u, float *out, long long count, void *stream)
 {
-    QBM_CHECK_ARG(x && out && count >= 0, "qbm_test_exp: bad argument");
+    QBM_CHECK_ARG(u && out && count >= 0, "qbm_test_neg_log: bad argument");
     if (count == 0) return QBM_OK;
-    test_exp_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, count);
-    QBM_LAUNCH_OK("test_exp_kernel");
+    test_neg_log_kernel<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(u, out, count);
+    QBM_LAUNCH_OK("test_neg_log_kernel");
     return QBM_OK;
 }

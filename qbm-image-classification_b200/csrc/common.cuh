@@ -53,23 +53,38 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{c0, c1, c2, c3};
 }
 
-// ---- exp_spec: FMA-only exp on (-87, 0], identical operation sequence to the replay oracle ---
-__device__ __forceinline__ float exp_spec(float x)
+// ---- neg_log_u32: FMA-only  -ln(u / 2^32)  for a 32-bit uniform, identical operation sequence to the
+// replay oracle (oracle/replay_sa.c).  The Metropolis test  u/2^32 < exp(-beta dE)  is evaluated in
+// the log domain,  dE < -ln(u/2^32) / beta,  so the transcendental is paid once per (chain, sweep,
+// variable) instead of once per re-evaluation of a proposal.  u = 0 -> +inf (bound falls back to the
+// threshold 44.36142/beta).
+__device__ __forceinline__ float neg_log_u32(uint32_t u)
 {
-    const float t = __fmul_rn(x, 1.44269504f);
-    const float k = rintf(t);
-    float f = __fmaf_rn(k, -0.693145751953125f, x);
-    f = __fmaf_rn(k, -1.42860677e-06f, f);
-    float p = 1.9875691500e-4f;
-    p = __fmaf_rn(p, f, 1.3981999507e-3f);
-    p = __fmaf_rn(p, f, 8.3334519073e-3f);
-    p = __fmaf_rn(p, f, 4.1665795894e-2f);
-    p = __fmaf_rn(p, f, 1.6666665459e-1f);
-    p = __fmaf_rn(p, f, 5.0000001201e-1f);
-    const float f2 = __fmul_rn(f, f);
-    float r = __fmaf_rn(p, f2, f);
-    r = __fadd_rn(r, 1.0f);
-    return __int_as_float(__float_as_int(r) + (__float2int_rn(k) << 23));
+    if (u == 0u) return __int_as_float(0x7f800000);
+    const float x = __uint2float_rn(u);                         // [1, 2^32], round to nearest even
+    const int bits = __float_as_int(x);
+    int e = (bits >> 23) - 127;
+    float m = __int_as_float((bits & 0x007fffff) | 0x3f800000);  // [1, 2)
+    if (m > 1.41421354f) { m = __fmul_rn(m, 0.5f); e += 1; }
+    const float f = __fadd_rn(m, -1.0f);                         // exact
+    const float z = __fmul_rn(f, f);
+    float y = 7.0376836292e-2f;
+    y = __fmaf_rn(y, f, -1.1514610310e-1f);
+    y = __fmaf_rn(y, f, 1.1676998740e-1f);
+    y = __fmaf_rn(y, f, -1.2420140846e-1f);
+    y = __fmaf_rn(y, f, 1.4249322787e-1f);
+    y = __fmaf_rn(y, f, -1.6668057665e-1f);
+    y = __fmaf_rn(y, f, 2.0000714765e-1f);
+    y = __fmaf_rn(y, f, -2.4999993993e-1f);
+    y = __fmaf_rn(y, f, 3.3333331174e-1f);
+    y = __fmul_rn(y, f);
+    y = __fmul_rn(y, z);
+    y = __fmaf_rn(-0.5f, z, y);
+    const float r = __fadd_rn(f, y);                             // ln(m)
+    const float E = (float)(32 - e);
+    float nl = __fmaf_rn(E, 0.693359375f, -r);
+    nl = __fmaf_rn(E, -2.12194440e-4f, nl);
+    return nl;
 }
 
 // Variable -> storage position inside a 128-variable window: the 4 variables a lane owns

@@ -2,7 +2,9 @@
 //
 // Replaces the Metropolis loop of dwave-neal 0.5.9 (cpu_sa.cpp) that the reference reaches through
 // src/qubo/sampler.py:31-33 and src/model/faster_dqbm.py:299-313.  The rule
-// is the reference's (fixed sweep order, threshold skip, dE<=0 auto-accept, u < exp(-beta dE)); the
+// is the reference's (fixed sweep order, threshold skip, dE<=0 auto-accept, u < exp(-beta dE) -- evaluated
+// in the log domain, dE < -ln(u)/beta, so a proposal that is re-evaluated after a neighbour flipped costs one
+// compare); the
 // layout is B200-first:
 //   * the chain's n local fields live in registers, 4*NW per lane (variable v = w*128 + k*32 + lane
 //     is register F[w][k] of `lane`); spins are 4*NW bits per lane
@@ -121,42 +123,50 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
         for (int s = 0; s < p.sweeps_per_beta; ++s, ++t) {
             for (int w = 0; w < nw_rt; ++w) {
                 if (rendezvous) __syncthreads();
-                // working copy of this window's four fields (register index must be static)
-                float Fc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                // working copy of this window's four fields (register index must be static); for a single
+                // window the fields themselves are the working copy
+                float Fc_store[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float (&Fc)[4] = *((NW == 1) ? &F[0] : &Fc_store);
+                if (NW > 1) {
 #pragma unroll
-                for (int w2 = 0; w2 < NW; ++w2)
-                    if (w2 == w) { Fc[0] = F[w2][0]; Fc[1] = F[w2][1]; Fc[2] = F[w2][2]; Fc[3] = F[w2][3]; }
+                    for (int w2 = 0; w2 < NW; ++w2)
+                        if (w2 == w) { Fc[0] = F[w2][0]; Fc[1] = F[w2][1]; Fc[2] = F[w2][2]; Fc[3] = F[w2][3]; }
+                }
                 uint32_t s4 = (uint32_t)(spins >> (w * 4)) & 15u;
+                // acceptance bounds of this lane's four proposals: flip <=> dE <= 0 or dE < bnd, with
+                // bnd = min(thr, -ln(u/2^32)/beta) drawn lazily (a pure function of (chain, sweep, variable))
                 bool have_rng = false;
-                uint32_t u[4] = {0u, 0u, 0u, 0u};
+                float bnd[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int k = 0; k < KS; ++k) {
                     const int vbase = w * 128 + k * 32;
                     if (vbase >= n) break;
-                    const bool inrange = (vbase + lane) < n;
-                    int pos = 0;
+                    const int rem = n - vbase;
+                    unsigned todo = rem >= 32 ? FULL : ((1u << rem) - 1u);   // proposals not yet passed, in sweep order
+                    const bool up0 = (s4 >> k) & 1u;
+                    unsigned upm = __ballot_sync(FULL, up0);                 // spins of the sub-window (warp-uniform)
+                    float sgn = up0 ? -2.0f : 2.0f;                          // dE = sgn * F
                     while (true) {
-                        const bool up = (s4 >> k) & 1u;
-                        const float dE = __fmul_rn(Fc[k], up ? -2.0f : 2.0f);
-                        const bool valid = inrange && (lane >= pos);
-                        bool acc = valid && (dE <= 0.0f);
-                        if (valid && (dE > 0.0f) && (dE < thr)) {
-                            if (!have_rng) {
+                        const float dE = __fmul_rn(Fc[k], sgn);
+                        if (!have_rng) {
+                            const bool pend = (dE > 0.0f) && (dE < thr);
+                            if (__ballot_sync(FULL, pend) & todo) {
                                 const Philox4 o = philox4x32_10(c_lo, c_hi, t, (uint32_t)(w * 32 + lane), k0, k1);
-                                u[0] = o.x; u[1] = o.y; u[2] = o.z; u[3] = o.w;
+                                const uint32_t u[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                for (int q4 = 0; q4 < KS; ++q4) bnd[q4] = fminf(thr, __fdiv_rn(neg_log_u32(u[q4]), beta));
                                 have_rng = true;
                             }
-                            const float pe = exp_spec(-__fmul_rn(dE, beta));
-                            acc = __float2ull_rz(__fmul_rn(pe, 4294967296.0f)) > (unsigned long long)u[k];
                         }
-                        const unsigned m = __ballot_sync(FULL, acc);
+                        const bool acc = (dE <= 0.0f) || (dE < bnd[k]);
+                        const unsigned m = __ballot_sync(FULL, acc) & todo;
                         if (m == 0u) break;
-                        const int a = __ffs(m) - 1;                       // first accepted proposal in sweep order
-                        const unsigned upm = __ballot_sync(FULL, up);
-                        const float c = ((upm >> a) & 1u) ? -2.0f : 2.0f;  // -2 * s_a(old)
-                        if (lane == a) s4 ^= (1u << k);
+                        const int a = __ffs(m) - 1;                          // first accepted proposal in sweep order
+                        const float c = ((upm >> a) & 1u) ? -2.0f : 2.0f;     // -2 * s_a(old)
+                        upm ^= 1u << a;
+                        if (lane == a) sgn = -sgn;
                         const float *row = J + (size_t)(vbase + a) * (size_t)ld + lane * 4;
-                        {
+                        if (NW > 1) {
                             const float4 r = __ldg(reinterpret_cast<const float4 *>(row + w * 128));
                             Fc[0] = __fmaf_rn(c, r.x, Fc[0]);
                             Fc[1] = __fmaf_rn(c, r.y, Fc[1]);
@@ -164,9 +174,10 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
                             Fc[3] = __fmaf_rn(c, r.w, Fc[3]);
                         }
                         row_update<NW>(F, row, c);
-                        pos = a + 1;
+                        todo &= ~((2u << a) - 1u);
                         ++nacc;
                     }
+                    s4 = (s4 & ~(1u << k)) | (((upm >> lane) & 1u) << k);
                 }
                 spins = (spins & ~(15ull << (w * 4))) | ((unsigned long long)s4 << (w * 4));
             }
@@ -279,6 +290,17 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     p.init = init_states; p.out = states_out; p.counters = counters; p.flags = flags;
 
     const int nw = sa_variant_nw(n);
+    if (flags & 4u) {   // experiment: one big CTA per SM so that all resident chains share coupling rows in L1
+        switch (nw) {
+            case 2: return launch_sa<2, 4, 32, 1>(p, st);
+            case 3: return launch_sa<3, 4, 24, 1>(p, st);
+            case 4: return launch_sa<4, 4, 24, 1>(p, st);
+            case 5: return launch_sa<5, 4, 24, 1>(p, st);
+            case 6: return launch_sa<6, 4, 16, 1>(p, st);
+            case 8: return launch_sa<8, 4, 16, 1>(p, st);
+            default: break;
+        }
+    }
     if (n <= 32) return launch_sa<1, 1, 8, 4>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4>(p, st);
     switch (nw) {

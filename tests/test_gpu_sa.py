@@ -35,18 +35,19 @@ def test_device_philox_matches_oracle(qbm, oracle, cuda):
         assert got[i].tolist() == oracle.philox4x32_10(ctr[i], key[i]).tolist()
 
 
-def test_device_exp_spec_bit_exact(qbm, oracle, cuda):
+def test_device_neg_log_bit_exact(qbm, oracle, cuda):
     rng = np.random.default_rng(2)
-    x = -rng.uniform(0, 44.4, 20000).astype(np.float32)
-    x[:4] = [0.0, -1e-30, -44.36, -1.0]
-    xd = torch.from_numpy(x).to(cuda)
-    od = torch.empty_like(xd)
+    u = rng.integers(0, 2 ** 32, 20000, dtype=np.uint64).astype(np.uint32)
+    u[:8] = [0, 1, 2, 2 ** 32 - 1, 2 ** 32 - 129, 2 ** 31, 3037000500, 12345]
+    ud = torch.from_numpy(u.view(np.int32)).to(cuda)
+    od = torch.empty(u.size, dtype=torch.float32, device=cuda)
     L = qbm._lib.load()
-    qbm._lib.check(L.qbm_test_exp(xd.data_ptr(), od.data_ptr(), x.size, None))
+    qbm._lib.check(L.qbm_test_neg_log(ud.data_ptr(), od.data_ptr(), u.size, None))
     got = od.cpu().numpy()
-    ref = np.array([oracle.exp_spec(float(v)) for v in x], dtype=np.float32)
+    ref = np.array([oracle.neg_log_u32(int(v)) for v in u], dtype=np.float32)
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
-    assert np.max(np.abs(got - np.exp(x.astype(np.float64))) / np.exp(x.astype(np.float64))) < 2e-7
+    fin = u > 0
+    assert np.max(np.abs(got[fin] + np.log(u[fin].astype(np.float64) / 2.0 ** 32))) < 2.5e-6
 
 
 @pytest.mark.parametrize("n,reads,sweeps,density", [

@@ -13,12 +13,18 @@ def test_philox_known_answers(oracle):
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
-def test_exp_spec_accuracy(oracle):
-    xs = -np.random.default_rng(0).uniform(0, 44.36, 20000).astype(np.float32)
-    got = np.array([oracle.exp_spec(float(x)) for x in xs])
-    ref = np.exp(xs.astype(np.float64))
-    assert np.max(np.abs(got - ref) / ref) < 2e-7
-    assert oracle.exp_spec(0.0) == 1.0
+def test_neg_log_u32_accuracy(oracle):
+    """-ln(u/2^32): the log-domain form of the Metropolis test."""
+    rng = np.random.default_rng(0)
+    us = np.concatenate([rng.integers(1, 2 ** 32, 20000), 2 ** rng.integers(0, 32, 200) + rng.integers(0, 3, 200),
+                         [1, 2, 3, 2 ** 32 - 1, 2 ** 32 - 300, 2 ** 31, 2 ** 31 - 1]]).astype(np.uint64)
+    got = np.array([oracle.neg_log_u32(int(u)) for u in us])
+    ref = -np.log(us.astype(np.float64) / 2.0 ** 32)
+    # absolute error: fp32 rounding of u (2^-24 relative) plus the polynomial; tiny against the smallest dE scale
+    assert np.max(np.abs(got - ref)) < 2.5e-6
+    assert np.all(got >= 0.0)
+    assert oracle.neg_log_u32(0) == np.inf
+    assert abs(oracle.neg_log_u32(1) - 32 * np.log(2)) < 2e-6
 
 
 def test_spin_energy_identity_and_offset(oracle):
