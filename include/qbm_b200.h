@@ -74,6 +74,10 @@ int qbm_qubo_to_ising(const double *Q, int n, long long batch, float *J_out, flo
  *   flags        bit 0: disable the per-window CTA rendezvous (debug / A-B measurements)
  *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
  *                       stream, as the reference's fixed per-call seed does)
+ *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed
+ *                       by TMA through a shared-memory ring; identical trajectories);
+ *                       bits 8..15: its dense/sparse update switch in percent of flipped (chain, variable)
+ *                       pairs per 32-variable sub-window (0 = default 40)
  */
 size_t qbm_sa_workspace_bytes(int n, long long batch_q);
 int qbm_sa_sample(const float *J, const float *h, int n, int ldj, long long batch_q,

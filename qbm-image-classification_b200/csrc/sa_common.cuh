@@ -1,0 +1,31 @@
+// Shared declarations of the two SA sampler kernels (sa_kernel.cu: one warp per chain; sa_tile.cu: a
+// register tile of T chains per CTA with coupling rows streamed through a TMA ring).
+#pragma once
+#include "common.cuh"
+
+struct SaParams {
+    const float *Jp;          // [batch_q, n, ld]  columns in p128 order, rows zero-padded to ld
+    const float *hp;          // [batch_q, ld]     p128 order, zero-padded
+    const float *Jnat;        // [batch_q, n, ldj] the caller's natural-order couplings (diagonal blocks of the tile kernel)
+    int ldj;
+    const float *beta;        // [batch_q or 1, num_betas]
+    long long beta_stride;
+    int num_betas;
+    int sweeps_per_beta;
+    int n;
+    int ld;
+    long long num_reads;
+    long long total_chains;   // batch_q * num_reads
+    unsigned long long seed;
+    unsigned long long chain_offset;
+    const int8_t *init;       // nullable [total_chains, n]
+    int8_t *out;              // [total_chains, n]
+    unsigned long long *counters;
+    unsigned flags;
+    long long batch_q;
+};
+
+// sa_tile.cu
+bool sa_tile_supported(int n);
+int sa_tile_ld(int n);
+int sa_tile_launch(const SaParams &p, cudaStream_t st);

@@ -18,28 +18,9 @@
 //     first accepted proposal of the sub-window is found with one ballot, every earlier proposal is
 //     a rejection that changes nothing, and evaluation restarts right after the flipped variable.
 //     The trajectory is therefore exactly the sequential one (oracle/replay_sa.c).
-#include "common.cuh"
+#include "sa_common.cuh"
 
 namespace {
-
-struct SaParams {
-    const float *Jp;          // [batch_q, n, ld]  columns in p128 order, rows zero-padded to ld
-    const float *hp;          // [batch_q, ld]     p128 order, zero-padded
-    const float *beta;        // [batch_q or 1, num_betas]
-    long long beta_stride;
-    int num_betas;
-    int sweeps_per_beta;
-    int n;
-    int ld;
-    long long num_reads;
-    long long total_chains;   // batch_q * num_reads
-    unsigned long long seed;
-    unsigned long long chain_offset;
-    const int8_t *init;       // nullable [total_chains, n]
-    int8_t *out;              // [total_chains, n]
-    unsigned long long *counters;
-    unsigned flags;
-};
 
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -276,7 +257,10 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
         return QBM_EWORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    const int ld = sa_ld(n);
+    // kernel choice: the warp-per-chain kernel is the default (faster at every size measured in round 1:
+    // 23.3 vs 15.4 G spin-updates/s at n = 2048); flag bit 4 selects the chain-tile kernel (sa_tile.cu)
+    const bool tile = (flags & 16u) != 0u && sa_tile_supported(n);
+    const int ld = tile ? sa_tile_ld(n) : sa_ld(n);
     float *Jp = reinterpret_cast<float *>(workspace);
     float *hp = Jp + (size_t)batch_q * (size_t)n * (size_t)ld;
 
@@ -288,19 +272,10 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     p.sweeps_per_beta = sweeps_per_beta; p.n = n; p.ld = ld; p.num_reads = num_reads;
     p.total_chains = batch_q * num_reads; p.seed = seed; p.chain_offset = chain_offset;
     p.init = init_states; p.out = states_out; p.counters = counters; p.flags = flags;
+    p.Jnat = J; p.ldj = ldj; p.batch_q = batch_q;
+    if (tile) return sa_tile_launch(p, st);
 
     const int nw = sa_variant_nw(n);
-    if (flags & 4u) {   // experiment: one big CTA per SM so that all resident chains share coupling rows in L1
-        switch (nw) {
-            case 2: return launch_sa<2, 4, 32, 1>(p, st);
-            case 3: return launch_sa<3, 4, 24, 1>(p, st);
-            case 4: return launch_sa<4, 4, 24, 1>(p, st);
-            case 5: return launch_sa<5, 4, 24, 1>(p, st);
-            case 6: return launch_sa<6, 4, 16, 1>(p, st);
-            case 8: return launch_sa<8, 4, 16, 1>(p, st);
-            default: break;
-        }
-    }
     if (n <= 32) return launch_sa<1, 1, 8, 4>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4>(p, st);
     switch (nw) {

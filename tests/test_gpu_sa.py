@@ -103,6 +103,59 @@ def test_sharding_invariance(qbm, cuda):
     assert torch.equal(full, nosync)
 
 
+# ---- the chain-tile kernel (sa_tile.cu): same trajectories, rows shared by 16 chains -------------------
+TILE, WARP = 16, 8      # qbm_sa_sample flag bits 4 / 3: force the chain-tile / the warp-per-chain kernel
+
+
+@pytest.mark.parametrize("n,reads,sweeps,density", [
+    (1, 5, 50, 1.0), (7, 16, 200, 1.0), (33, 17, 300, 1.0), (100, 40, 400, 1.0), (128, 16, 300, 1.0),
+    (129, 9, 300, 1.0), (193, 35, 1000, 0.89), (300, 6, 200, 1.0), (522, 20, 1000, 1.0), (700, 4, 100, 1.0),
+    (1000, 33, 100, 1.0), (1025, 3, 100, 1.0), (1200, 16, 100, 1.0), (1500, 3, 100, 1.0), (1800, 5, 60, 0.3),
+    (2048, 18, 1000, 1.0),
+])
+def test_tile_kernel_bit_exact_vs_replay(qbm, oracle, cuda, n, reads, sweeps, density):
+    """K1b: 16 chains per CTA in lock-step, coupling rows through the TMA ring -- every bit of every read
+    equals the sequential CPU replay, for dense (hot) and sparse (cold) update paths alike."""
+    Q = random_qubo(n, seed=19 + n, density=density)
+    h, J, betas, spb = _prep(qbm, Q, sweeps)
+    seed, off = 0x1234ABCD5678EF01 ^ n, 7 * n
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J, h, betas))
+    res = qbm.sa_sample(Jd, hd, bd, spb, reads, seed, chain_offset=off, count=True, flags=TILE)
+    got = res.states.cpu().numpy()[0]
+    ref, counters = oracle.replay_sample(J, h, betas, spb, seed, off, reads)
+    assert np.array_equal(got, ref)
+    acc = res.accepted.cpu().numpy().astype(np.uint64)
+    assert int(acc[0]) == int(counters[0])
+    assert int(acc[1]) == reads * n * len(betas) * spb
+    # the dense/sparse switch is a performance choice only: always-sparse and always-dense agree
+    for pct in (1, 255):
+        alt = qbm.sa_sample(Jd, hd, bd, spb, reads, seed, chain_offset=off, flags=TILE | (pct << 8)).states
+        assert torch.equal(alt, res.states), f"dense threshold {pct}"
+
+
+def test_tile_kernel_batch_init_states_and_shared_stream(qbm, oracle, cuda):
+    B, n, reads, sweeps = 4, 150, 21, 300
+    Qs = np.stack([random_qubo(n, seed=100 + b, scale=1.0 + b) for b in range(B)])
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
+    init = np.stack([qbm.ising.initial_states_numpy(44 + b, reads, n) for b in range(B)])
+    J32, h32, b32 = J.astype(np.float32), h.astype(np.float32), betas.astype(np.float32)
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J32, h32, b32))
+    got = qbm.sa_sample(Jd, hd, bd, spb, reads, 77, init_states=torch.from_numpy(init).to(cuda), flags=TILE).states.cpu().numpy()
+    for b in range(B):
+        ref, _ = oracle.replay_sample(J32[b], h32[b], b32[b], spb, 77, b * reads, reads, init01=init[b])
+        assert np.array_equal(got[b], ref), f"problem {b}"
+    # flag bit 1: every problem sees the stream of read r (the reference's fixed per-call seed)
+    got = qbm.sa_sample(Jd, hd, bd, spb, reads, 77, chain_offset=5, flags=TILE | 2).states.cpu().numpy()
+    for b in range(B):
+        ref, _ = oracle.replay_sample(J32[b], h32[b], b32[b], spb, 77, 5, reads)
+        assert np.array_equal(got[b], ref), f"problem {b} (shared stream)"
+    # both kernels agree with each other on the default path too
+    a = qbm.sa_sample(Jd, hd, bd, spb, reads, 3, flags=TILE).states
+    w = qbm.sa_sample(Jd, hd, bd, spb, reads, 3, flags=WARP).states
+    assert torch.equal(a, w)
+
+
 @pytest.mark.parametrize("n,R,B", [(1, 3, 1), (24, 100, 3), (34, 77, 2), (193, 130, 1), (522, 65, 1), (2048, 70, 1)])
 def test_energies_vs_oracle(qbm, oracle, cuda, n, R, B):
     rng = np.random.default_rng(n)
