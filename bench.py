@@ -250,13 +250,12 @@ def run_gpu(args):
                 tt = torch.tensor([tms, te2e], dtype=torch.float64, device=dev)
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
                 tms, te2e = float(tt[0]), float(tt[1])
-            # C2 has no cross-rank exchange in this round: N independent replicas
             imgs = float(world) * args.train_steps * batch
             key = cfg if cfg != "c2" else f"c2_{mode}"
             train[key] = {"workload": BT.CONFIGS[cfg][0] + (f" [{mode} step]" if cfg == "c2" else ""),
                           "metric": "train images/sec", "value": imgs / (tms * 1e-3), "unit": "images/s",
                           "batch_per_gpu": batch, "steps": args.train_steps, "ms_per_step": tms / args.train_steps,
-                          "scaling": "weak" if cfg != "c2" else "replicas only",
+                          "scaling": "weak",
                           "e2e": {"value": imgs / te2e, "unit": "images/s", "h2d_bytes_per_step": th2d,
                                   "d2h_bytes_per_step": 8}}
 

@@ -85,7 +85,8 @@ def make_model(cfg, qbm, dev, pg=None):
                                pooling_type="deterministic", stride=1, sequential_layer_sizes=[128], is_restricted=False,
                                hidden_bias_type="shared", solver="SA", anneal=1000, seed=44, device=dev, process_group=pg)
     if cfg == "c2":
-        return qbm.B200ClassificationRBM(784, 500, k=1, num_classes=10, learning_rate=0.05, seed=19, device=dev)
+        return qbm.B200ClassificationRBM(784, 500, k=1, num_classes=10, learning_rate=0.05, seed=19, device=dev,
+                                         process_group=pg)
     raise ValueError(cfg)
 
 
@@ -97,20 +98,20 @@ def _step_fn(cfg, model, mode):
                                                                first_image=off)
     if cfg == "c2":
         if mode == "cd1":
-            return lambda X, Y, gb, off: model.cd1_training(X, Y)
-        return lambda X, Y, gb, off: model.discriminative_training(X, Y)[0].item()
+            return lambda X, Y, gb, off: model.cd1_training(X, Y, global_batch=gb)
+        return lambda X, Y, gb, off: model.discriminative_training(X, Y, global_batch=gb)[0].item()
     raise ValueError(cfg)
 
 
 def gpu_train_rate(cfg, qbm, torch, dev, world, rank, barrier, batch, steps, warmup, pg=None, mode="disc"):
     """(images/s device-resident inputs, images/s end to end from host buffers, ms/step) for one config."""
-    model = make_model(cfg, qbm, dev, pg if cfg != "c2" else None)
+    model = make_model(cfg, qbm, dev, pg)
     nsteps = warmup + 2 * steps
     X, Y, _ = make_data(cfg, batch * nsteps, seed=19 + rank)
     if cfg == "c2":
         Y = Y.astype(np.int32)
     fn = _step_fn(cfg, model, mode)
-    gb = batch * world if cfg != "c2" else batch
+    gb = batch * world
     sl = lambda a, i: a[i * batch:(i + 1) * batch]
     # device-resident inputs: staged before the timed region
     Xd = torch.from_numpy(np.ascontiguousarray(X)).to(dev)

@@ -8,7 +8,7 @@ Public surface (mirrors the reference's call boundary):
 * ``shims.install()``          ``dimod`` / ``neal`` duck types for ``Disc_QBM`` (faster_dqbm.py)
 * ``sa_sample / qubo_energies / phase_stats``  batched device-level calls over the C ABI
 """
-from . import _lib, conv_deep_qbm, disc_qbm, ising, rbm, sampler, shims  # noqa: F401
+from . import _lib, conv_deep_qbm, disc_qbm, dist, ising, rbm, sampler, shims  # noqa: F401
 from .conv_deep_qbm import ConvDeepQBM  # noqa: F401
 from .rbm import B200ClassificationRBM, gemm_tf32  # noqa: F401
 from .disc_qbm import DiscQBM  # noqa: F401

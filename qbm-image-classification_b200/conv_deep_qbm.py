@@ -23,7 +23,7 @@ import random
 import numpy as np
 import torch
 
-from . import _lib, ising, sampler as _s
+from . import _lib, dist as _d, ising, sampler as _s
 from .disc_qbm import schedule_device
 
 
@@ -271,21 +271,13 @@ class ConvDeepQBM:
         err = self._errors(patches, Ylab, mc, sc, mu, su)
         names = [k for k in ("b_conv", "b_seq", "b_out", "kernel", "W_seq", "W_intra", "W_hy", "W_oo")
                  if k in err and not (k == "W_intra" and self.is_restricted)]
-        parts = []
+        parts, targets = [], []
         for k in names:
-            parts += [t.reshape(-1) for t in (err[k] if isinstance(err[k], list) else [err[k]])]
-        flat = torch.cat(parts + [loss_sum.reshape(1)])
-        if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+            parts += err[k] if isinstance(err[k], list) else [err[k]]
+            targets += self._p[k] if isinstance(self._p[k], list) else [self._p[k]]
+        flat = _d.all_reduce_sum_(_d.pack(parts + [loss_sum]), self.pg)
         gb = float(global_batch if global_batch is not None else B)
-        pos = 0
-        for k in names:
-            tgt = self._p[k] if isinstance(self._p[k], list) else [self._p[k]]
-            for t in tgt:
-                cnt = t.numel()
-                t -= lr * (flat[pos:pos + cnt].reshape(t.shape) / gb)
-                pos += cnt
+        _d.sgd_apply_(targets, flat, lr, gb)
         self.step_count += 1
         return float(flat[-1].item() / max(1.0, gb))
 

@@ -24,7 +24,7 @@ import random
 import numpy as np
 import torch
 
-from . import ising, sampler as _s
+from . import dist as _d, ising, sampler as _s
 
 
 def geomspace_device(lo: torch.Tensor, hi: torch.Tensor, num: int) -> torch.Tensor:
@@ -237,18 +237,11 @@ class DiscQBM:
             # discriminative_qbm.py:875-951 has its NLL commented out: total_nll_loss stays 0
             loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
         names = [k for k in ("b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh") if k in err]
-        flat = torch.cat([err[k].reshape(-1) for k in names] + [loss_sum.reshape(1)])
-        if self.pg is not None:
-            import torch.distributed as dist
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        flat = _d.all_reduce_sum_(_d.pack([err[k] for k in names] + [loss_sum]), self.pg)
         gb = float(global_batch if global_batch is not None else B)
-        pos = 0
-        for k in names:
-            cnt = err[k].numel()
-            self._p[k] -= learning_rate * (flat[pos:pos + cnt].reshape(err[k].shape) / gb)
-            if k == "b_o":
-                ebo = flat[pos:pos + cnt] / gb
-            pos += cnt
+        _d.sgd_apply_([self._p[k] for k in names], flat, learning_rate, gb)
+        pos = sum(err[k].numel() for k in names[:names.index("b_o")])
+        ebo = flat[pos:pos + err["b_o"].numel()] / gb
         avg_loss = float(flat[-1].item() / gb)
         self.nll_per_batch.append(avg_loss)
         self.step_count += 1

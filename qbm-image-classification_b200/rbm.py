@@ -51,7 +51,7 @@ def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha=1.0, beta=0.0, Cin=None, b
 
 class B200ClassificationRBM:
     def __init__(self, num_visible, num_hidden, k, num_classes=2, learning_rate=0.05, sparse_constant=0.00,
-                 use_cuda=True, seed=42, device=None):
+                 use_cuda=True, seed=42, device=None, process_group=None):
         # same RNG protocol as the reference (:14-15, :26-30): CPU generators, then moved to the device
         np.random.seed(seed)
         torch.manual_seed(seed)
@@ -64,6 +64,7 @@ class B200ClassificationRBM:
         if self.num_classes > 32:
             raise ValueError("the fused class kernels support at most 32 classes")
         self.device = _require_cuda(device)
+        self.pg = process_group            # data-parallel minibatches: deltas are all-reduced
         V, H, C = self.num_visible, self.num_hidden, self.num_classes
         w = torch.randn(V, H) * 0.1
         self._W = _padded(V, H, self.device); self._W[:, :H] = w.to(self.device)
@@ -130,6 +131,46 @@ class B200ClassificationRBM:
             rc = fn(*args, _stream_ptr(self.device))
         _lib.check(rc)
 
+    # ---- data-parallel minibatches ---------------------------------------------------------------------
+    def _world(self):
+        if self.pg is None:
+            return 1
+        import torch.distributed as dist
+        return dist.get_world_size(self.pg)
+
+    def _rank(self):
+        if self.pg is None:
+            return 0
+        import torch.distributed as dist
+        return dist.get_rank(self.pg)
+
+    def _data_parallel(self, run, B_local, global_batch, loss):
+        """The step kernels update the parameters in place with gradient sums scaled by lr / B.  For a sharded
+        minibatch every rank runs the step on its shard with lr * B_local / B_global (and no decay), the parameter
+        deltas are all-reduced (sum) and applied to the pre-step parameters -- the update of the whole minibatch
+        -- then the decay (sparse_constant) is applied once and W^T is refreshed."""
+        import torch.distributed as dist
+        gb = float(global_batch if global_batch is not None else B_local * self._world())
+        params = [self._W, self._U, self.visible_bias, self.hidden_bias, self.class_bias]
+        before = [t.clone() for t in params]
+        run(self.learning_rate * B_local / gb, 0.0)
+        parts = [(c - b).reshape(-1) for c, b in zip(params, before)]
+        if loss is not None:
+            parts.append(loss.reshape(1) * (B_local / gb))
+        delta = torch.cat(parts)
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.pg)
+        pos = 0
+        for c, b in zip(params, before):
+            c.copy_(b + delta[pos:pos + c.numel()].view_as(c))
+            pos += c.numel()
+        if loss is not None:
+            loss.copy_(delta[pos:pos + 1])
+        if self.sparse_constant:
+            for t in (self.visible_bias, self.hidden_bias, self.class_bias):
+                t -= self.sparse_constant
+        self._Wt.zero_()
+        self._Wt[:, :self.num_visible] = self._W[:, :self.num_hidden].t()
+
     # ---- Gibbs primitives (:43-60) --------------------------------------------------------------------
     def sample_hidden(self, visible_activations, class_activations):
         L = _lib.load()
@@ -171,8 +212,9 @@ class B200ClassificationRBM:
         return P[:, :self.num_classes]
 
     # ---- training steps -----------------------------------------------------------------------------------
-    def discriminative_training(self, input_data, class_label, factor=1):
-        """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors."""
+    def discriminative_training(self, input_data, class_label, factor=1, global_batch=None):
+        """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors.  With a process group
+        ``input_data`` is this rank's shard of a minibatch of ``global_batch`` rows (default: shard x world)."""
         L = _lib.load()
         x = self._pad_rows(input_data, self.num_visible)
         B = x.shape[0]
@@ -183,25 +225,40 @@ class B200ClassificationRBM:
         pred = torch.empty(B, dtype=torch.int32, device=self.device)
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
         ws = self._workspace(B)
-        self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
-                   self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), x.data_ptr(), y.data_ptr(), B, self.num_visible,
-                   self.num_hidden, self.num_classes, float(self.learning_rate), float(factor), float(self.sparse_constant),
-                   probs.data_ptr(), pred.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+
+        def run(lr, sparse):
+            self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), x.data_ptr(),
+                       y.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(lr), float(factor),
+                       float(sparse), probs.data_ptr(), pred.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+
+        if self.pg is None:
+            run(self.learning_rate, self.sparse_constant)
+        else:
+            self._data_parallel(run, B, global_batch, loss)
         self._step += 1
         return loss[0], pred.to(torch.int64), probs[:, :self.num_classes]
 
-    def cd1_training(self, input_data, class_label):
-        """One CD-1 step (k = 1) on a minibatch; parameters updated in place."""
+    def cd1_training(self, input_data, class_label, global_batch=None):
+        """One CD-1 step (k = 1) on a minibatch (or this rank's shard of it); parameters updated in place."""
         L = _lib.load()
         v0 = self._pad_rows(input_data, self.num_visible)
         B = v0.shape[0]
         y0 = self._labels(class_label, B)
         ws = self._workspace(B)
-        self._call(L.qbm_rbm_cd1_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
-                   self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(), y0.data_ptr(), B, self.num_visible,
-                   self.num_hidden, self.num_classes, float(self.learning_rate), float(self.sparse_constant),
-                   ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(self._step & 0x3FFFFFFF),
-                   ws.data_ptr(), ws.numel() * 4)
+        # sharded minibatches draw from disjoint Philox streams: the step counter is offset by the rank
+        stream = (self._step * self._world() + self._rank()) & 0x3FFFFFFF
+
+        def run(lr, sparse):
+            self._call(L.qbm_rbm_cd1_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(),
+                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(lr), float(sparse),
+                       ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream), ws.data_ptr(), ws.numel() * 4)
+
+        if self.pg is None:
+            run(self.learning_rate, self.sparse_constant)
+        else:
+            self._data_parallel(run, B, global_batch, None)
         self._step += 1
 
     def predict(self, input_data):

@@ -1,0 +1,98 @@
+"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): data-parallel training steps equal the single-GPU step
+on the whole minibatch, and read-sharded sampling equals one launch."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import qbm_b200
+    from qbm_b200.dist import shard_range
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    res = {}
+    try:
+        pg = dist.group.WORLD
+        # ---- Disc_QBM (C1 shapes): sharded minibatch + all-reduce == whole minibatch on one GPU ----
+        g = np.load(os.path.join(G, "disc_qbm_loop_onehot.npz"))
+        X, Y = g["X"], g["Y"]
+        mk = lambda pg_: (np.random.seed(19), qbm_b200.DiscQBM(dim_input=16, num_classes=10, use_one_hot_encoding=True,
+                          n_hidden_nodes=24, sample_count=60, anneal_steps=200, seed=19, stats_mode="loop", device=dev,
+                          process_group=pg_))[1]
+        single, dp = mk(None), mk(pg)
+        single.train_for_one_iteration(X, Y, 0.1)
+        lo, hi = shard_range(len(X), world, rank)
+        dp.train_for_one_iteration(X[lo:hi], Y[lo:hi], 0.1, global_batch=len(X), first_image=lo)
+        a, b = single.get_params(), dp.get_params()
+        res["disc"] = max(float(np.abs(a[k] - b[k]).max()) for k in a)
+        # ---- Conv_Deep_QBM ----
+        g = np.load(os.path.join(G, "convdeep_binary.npz"))
+        X, Y = g["X"], g["Y"]
+        mk = lambda pg_: qbm_b200.ConvDeepQBM(100, 1, image_shape=(10, 10), kernel_size=3, pooling_size=2,
+                                              sequential_layer_sizes=[12], hidden_bias_type="shared", anneal=200, seed=44,
+                                              device=dev, process_group=pg_)
+        single, dp = mk(None), mk(pg)
+        l1 = single.train_one_iteration(X, Y, 40, 1.0, 0.05)
+        lo, hi = shard_range(len(X), world, rank)
+        l2 = dp.train_one_iteration(X[lo:hi], Y[lo:hi], 40, 1.0, 0.05, global_batch=len(X), first_image=lo)
+        a, b = single.get_params(), dp.get_params()
+        d = 0.0
+        for k in a:
+            for u, v in zip(a[k] if isinstance(a[k], list) else [a[k]], b[k] if isinstance(b[k], list) else [b[k]]):
+                d = max(d, float(np.abs(u - v).max()))
+        res["convdeep"] = max(d, abs(l1 - l2))
+        # ---- ClassificationRBM discriminative step (float32) ----
+        rng = np.random.default_rng(3)
+        xb = (rng.random((64, 784)) < 0.3).astype(np.float32)
+        yb = rng.integers(0, 10, 64)
+        mk = lambda pg_: qbm_b200.B200ClassificationRBM(784, 500, 1, num_classes=10, learning_rate=0.05, seed=7, device=dev,
+                                                        process_group=pg_)
+        single, dp = mk(None), mk(pg)
+        e1, _, _ = single.discriminative_training(xb, yb)
+        lo, hi = shard_range(64, world, rank)
+        e2, _, _ = dp.discriminative_training(xb[lo:hi], yb[lo:hi], global_batch=64)
+        res["rbm"] = max(float((single.weights - dp.weights).abs().max()), float((single.class_weights - dp.class_weights).abs().max()),
+                         float((single.hidden_bias - dp.hidden_bias).abs().max()), abs(float(e1) - float(e2)))
+        # ---- sampler: reads sharded by global index == one launch ----
+        Q = np.triu(rng.uniform(-1, 1, (150, 150)))
+        full, _, _ = qbm_b200.sample_qubo_batch(Q, 64, 200, seed=9, initial_states_generator="philox", device=dev,
+                                                return_energy=False)
+        lo, hi = shard_range(64, world, rank)
+        part, _, _ = qbm_b200.sample_qubo_batch(Q, hi - lo, 200, seed=9, initial_states_generator="philox", device=dev,
+                                                return_energy=False, chain_offset=lo)
+        res["sa"] = float(np.abs(full[0, lo:hi].astype(int) - part[0].astype(int)).max())
+        np.save(os.path.join(out_dir, f"rank{rank}.npy"), res, allow_pickle=True)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_data_parallel_equals_single_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        res = np.load(tmp_path / f"rank{r}.npy", allow_pickle=True).item()
+        assert res["disc"] < 1e-12, res          # float64 statistics: only the all-reduce summation order differs
+        assert res["convdeep"] < 1e-9, res
+        assert res["rbm"] < 2e-5, res            # float32 parameters, TF32 products
+        assert res["sa"] == 0.0, res             # bit-identical reads
