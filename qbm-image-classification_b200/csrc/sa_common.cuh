@@ -29,3 +29,7 @@ struct SaParams {
 bool sa_tile_supported(int n);
 int sa_tile_ld(int n);
 int sa_tile_launch(const SaParams &p, cudaStream_t st);
+
+// sa_multi.cu
+bool sa_multi_supported(int nw, long long num_reads);
+int sa_multi_launch(const SaParams &p, int nw, cudaStream_t st);

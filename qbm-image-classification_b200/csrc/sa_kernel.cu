@@ -276,6 +276,7 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     if (tile) return sa_tile_launch(p, st);
 
     const int nw = sa_variant_nw(n);
+    if ((flags & 32u) && sa_multi_supported(nw, num_reads)) return sa_multi_launch(p, nw, st);
     if (n <= 32) return launch_sa<1, 1, 8, 4>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4>(p, st);
     switch (nw) {

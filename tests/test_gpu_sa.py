@@ -156,6 +156,49 @@ def test_tile_kernel_batch_init_states_and_shared_stream(qbm, oracle, cuda):
     assert torch.equal(a, w)
 
 
+# ---- the multi-chain warp kernel (sa_multi.cu): a warp anneals T chains and shares row loads ---------------
+MULTI = 32      # qbm_sa_sample flag bit 5
+
+
+@pytest.mark.parametrize("n,reads,sweeps,density", [
+    (129, 9, 300, 1.0), (193, 35, 1000, 0.89), (256, 8, 200, 1.0), (300, 6, 200, 1.0), (400, 5, 150, 1.0),
+    (522, 21, 1000, 1.0), (700, 7, 100, 1.0), (1000, 9, 100, 1.0), (1025, 3, 100, 1.0), (1200, 5, 100, 1.0),
+    (1500, 3, 100, 1.0), (1800, 5, 60, 0.3), (2048, 7, 1000, 1.0),
+])
+def test_multi_kernel_bit_exact_vs_replay(qbm, oracle, cuda, n, reads, sweeps, density):
+    """K1c: T chains per warp with shared coupling-row loads -- every bit of every read equals the sequential
+    CPU replay (read counts that do not divide by T included)."""
+    Q = random_qubo(n, seed=19 + n, density=density)
+    h, J, betas, spb = _prep(qbm, Q, sweeps)
+    seed, off = 0x1234ABCD5678EF01 ^ n, 7 * n
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J, h, betas))
+    res = qbm.sa_sample(Jd, hd, bd, spb, reads, seed, chain_offset=off, count=True, flags=MULTI)
+    got = res.states.cpu().numpy()[0]
+    ref, counters = oracle.replay_sample(J, h, betas, spb, seed, off, reads)
+    assert np.array_equal(got, ref)
+    acc = res.accepted.cpu().numpy().astype(np.uint64)
+    assert int(acc[0]) == int(counters[0])
+    assert int(acc[1]) == reads * n * len(betas) * spb
+
+
+def test_multi_kernel_batch_init_states_and_shared_stream(qbm, oracle, cuda):
+    B, n, reads, sweeps = 4, 150, 21, 300
+    Qs = np.stack([random_qubo(n, seed=100 + b, scale=1.0 + b) for b in range(B)])
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
+    init = np.stack([qbm.ising.initial_states_numpy(44 + b, reads, n) for b in range(B)])
+    J32, h32, b32 = J.astype(np.float32), h.astype(np.float32), betas.astype(np.float32)
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J32, h32, b32))
+    got = qbm.sa_sample(Jd, hd, bd, spb, reads, 77, init_states=torch.from_numpy(init).to(cuda), flags=MULTI).states.cpu().numpy()
+    for b in range(B):
+        ref, _ = oracle.replay_sample(J32[b], h32[b], b32[b], spb, 77, b * reads, reads, init01=init[b])
+        assert np.array_equal(got[b], ref), f"problem {b}"
+    got = qbm.sa_sample(Jd, hd, bd, spb, reads, 77, chain_offset=5, flags=MULTI | 2).states.cpu().numpy()
+    for b in range(B):
+        ref, _ = oracle.replay_sample(J32[b], h32[b], b32[b], spb, 77, 5, reads)
+        assert np.array_equal(got[b], ref), f"problem {b} (shared stream)"
+
+
 @pytest.mark.parametrize("n,R,B", [(1, 3, 1), (24, 100, 3), (34, 77, 2), (193, 130, 1), (522, 65, 1), (2048, 70, 1)])
 def test_energies_vs_oracle(qbm, oracle, cuda, n, R, B):
     rng = np.random.default_rng(n)
