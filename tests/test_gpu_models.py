@@ -188,3 +188,42 @@ def test_device_schedule_matches_numpy(qbm, cuda):
     assert spb == spb2 and got.shape == (5, 1000)
     assert np.allclose(got.cpu().numpy(), ref.astype(np.float32), rtol=3e-7, atol=0)
     assert got[4, 0].item() == np.float32(0.1) and got[4, -1].item() == 1.0
+
+
+def test_disc_qbm_training_accuracy_within_1pp_of_cpu_reference_loop(qbm, oracle, cuda):
+    """north_star correctness criterion 4: train the same Disc_QBM (same initial draws, same minibatches, same
+    learning rule) once through the batched GPU step and once through the reference's per-image loop restated on
+    the CPU (oracle/model_oracle.py + the neal restatement), then compare test accuracy.  The samplers use
+    different random streams, so the comparison is statistical: |acc_gpu - acc_cpu| <= 1 pp on 600 test images."""
+    rng = np.random.default_rng(123)
+    di, h, n_train, n_test = 12, 4, 96, 600
+    w_true = np.zeros(di)
+    w_true[:3] = [2.0, -1.5, 1.0]                         # three informative inputs, nine distractors
+
+    def draw(num):
+        X = rng.random((num, di))
+        margin = (X - 0.5) @ w_true
+        keep = np.abs(margin) > 1.2                       # a wide margin: both loops reach ~99 %, so that the
+        return X[keep], (margin[keep] > 0).astype(np.float64)   # comparison is not dominated by sampling noise
+
+    Xtr, ytr = draw(40 * n_train); Xtr, ytr = Xtr[:n_train], ytr[:n_train]
+    Xte, yte = draw(40 * n_test); Xte, yte = Xte[:n_test], yte[:n_test]
+    assert len(Xtr) == n_train and len(Xte) == n_test
+    reads, sweeps, lr, batch, epochs, seed = 40, 200, 0.5, 16, 12, 21
+
+    np.random.seed(5)
+    m = qbm.DiscQBM(dim_input=di, num_classes=2, use_one_hot_encoding=False, n_hidden_nodes=h, restricted=False,
+                    sample_count=reads, anneal_steps=sweeps, beta_eff=1.0, seed=seed, stats_mode="loop")
+    p = m.get_params()
+    for _ in range(epochs):
+        for s in range(0, n_train, batch):
+            xb, yb = Xtr[s:s + batch], ytr[s:s + batch]
+            m.train_for_one_iteration(xb, yb, lr)
+            Sc = [oracle.sample_Q_reference(M.disc_qubo(p, x, y), reads, sweeps, seed=seed) for x, y in zip(xb, yb)]
+            Su = [oracle.sample_Q_reference(M.disc_qubo(p, x, None), reads, sweeps, seed=seed) for x in xb]
+            p = M.disc_train_step(p, xb, yb, Sc, Su, lr, "loop")
+    acc_gpu = float(np.mean(m.predict_batch(Xte) == yte))
+    pred_cpu = [M.disc_predict(oracle.sample_Q_reference(M.disc_qubo(p, x, None), reads, sweeps, seed=seed), 1, False) for x in Xte]
+    acc_cpu = float(np.mean(np.array(pred_cpu) == yte))
+    assert acc_cpu > 0.95 and acc_gpu > 0.95, (acc_gpu, acc_cpu)           # both learned the task
+    assert abs(acc_gpu - acc_cpu) <= 0.01 + 1e-9, (acc_gpu, acc_cpu)
