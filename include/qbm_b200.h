@@ -158,6 +158,30 @@ int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, floa
                      void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K7 / K8 / K9  the Disc_QBM training step around the sampler, one launch each per minibatch (float64).
+ * Parameters live in ONE flat buffer, which is also the layout of the error buffer:
+ *   [ b_h (h) | b_o (no) | W_vh ((no+di) x h) | W_vo (di x no) | W_oo (no x no) | W_hh (h x h; absent when restricted) ]
+ *   qbm_disc_param_count  number of elements of that buffer
+ *   qbm_disc_build_qubo   ref: create_qubo_matrix_from, src/model/faster_dqbm.py:225-284.  X [B, di]; Y [B, no] label
+ *                         rows (clamped phase, variables = hidden units) or NULL (unclamped, variables = outputs then
+ *                         hidden); Q_out [B, n, n] upper-triangular, divided by beta_eff
+ *   qbm_disc_errors       ref: get_average_configuration (src/model/discriminative_qbm.py:696-760; faster_mode = 0) or
+ *                         get_average_configuration_batch incl. its quirks (src/model/faster_dqbm.py:754-848; faster_mode
+ *                         = 1), summed over the B local images, clamped - unclamped, from the moments of K3:
+ *                         mean_c [B, h], second_c [B, h, h] (nullable when unused), mean_u [B, no+h], second_u
+ *                         [B, no+h, no+h].  err_out has qbm_disc_param_count + 1 elements; the last one is the NLL sum
+ *                         of faster_dqbm.py:972-994 (0 for faster_mode = 0, where the reference has it commented out)
+ *   qbm_sgd_apply         ref: faster_dqbm.py:1042-1059.  params[i] -= lr * (err[i] / batch)
+ */
+long long qbm_disc_param_count(int dim_input, int n_output, int n_hidden, int restricted);
+int qbm_disc_build_qubo(const double *params, int dim_input, int n_output, int n_hidden, int restricted, const double *X,
+                        const double *Y, long long B, double beta_eff, double *Q_out, void *stream);
+int qbm_disc_errors(int dim_input, int n_output, int n_hidden, int restricted, int faster_mode, const double *X,
+                    const double *Y, long long B, const double *mean_c, const double *second_c, const double *mean_u,
+                    const double *second_u, double *err_out, void *stream);
+int qbm_sgd_apply(double *params, const double *err, long long count, double lr, double batch, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * K6  Conv-Deep inference context for a minibatch: valid convolution with the shared kernel,
  * deterministic p x p pooling (argmin per window) and the input patch of every active unit.
  * ref: src/model/geometry.py:37-53 (conv2d_valid_stride), src/model/layers.py:65-84

@@ -24,7 +24,7 @@ import random
 import numpy as np
 import torch
 
-from . import dist as _d, ising, sampler as _s
+from . import _lib, dist as _d, ising, sampler as _s
 
 
 def geomspace_device(lo: torch.Tensor, hi: torch.Tensor, num: int) -> torch.Tensor:
@@ -93,7 +93,20 @@ class DiscQBM:
         W_oo = np.triu(np.random.uniform(-1, 1, (no, no)), k=1)
         b_h = np.random.uniform(-1, 1, h)
         b_o = np.random.uniform(-1, 1, no)
-        self._p = {}
+        # all parameters live in ONE flat float64 device buffer (the layout of include/qbm_b200.h, K7-K9);
+        # self._p holds views into it under the short names
+        shapes = [("b_h", (h,)), ("b_o", (no,)), ("W_vh", (no + di, h)), ("W_vo", (di, no)), ("W_oo", (no, no))]
+        if not restricted:
+            shapes.append(("W_hh", (h, h)))
+        total = sum(int(np.prod(sh)) for _, sh in shapes)
+        assert total == _lib.load().qbm_disc_param_count(di, no, h, int(self.restricted))
+        self._flat = torch.zeros(total, dtype=torch.float64, device=self.device)
+        self._p = {"W_hh": None}
+        pos = 0
+        for nm, sh in shapes:
+            cnt = int(np.prod(sh))
+            self._p[nm] = self._flat[pos:pos + cnt].view(sh)
+            pos += cnt
         self.set_params(W_vh=W_vh, W_vo=W_vo, W_oo=W_oo, b_h=b_h, b_o=b_o, W_hh=W_hh)
         self._init_cache = {}
         self.nll_per_batch = []
@@ -108,7 +121,14 @@ class DiscQBM:
 
     def set_params(self, **kw):
         for k, v in kw.items():
-            self._p[k] = None if v is None else torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device).clone()
+            if self._p.get(k) is None:
+                if v is not None:
+                    raise ValueError(f"{k} does not exist in a restricted model")
+                continue
+            v = torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device)
+            if v.shape != self._p[k].shape:
+                raise ValueError(f"{k}: expected shape {tuple(self._p[k].shape)}, got {tuple(v.shape)}")
+            self._p[k].copy_(v)
 
     def get_params(self) -> dict:
         return {k: (None if v is None else v.cpu().numpy()) for k, v in self._p.items()}
@@ -142,24 +162,24 @@ class DiscQBM:
         return self._to_dev(y_batch).reshape(B, self.n_output_nodes)
 
     def build_qubos(self, X: torch.Tensor, Y: torch.Tensor | None) -> torch.Tensor:
-        """Batched ``create_qubo_matrix_from``: float64 [B, n, n] on the device."""
-        p, no, h = self._p, self.n_output_nodes, self.n_hidden_nodes
+        """Batched ``create_qubo_matrix_from`` (K7): float64 [B, n, n] on the device."""
+        no, h, di = self.n_output_nodes, self.n_hidden_nodes, self.dim_input
+        X = X.to(torch.float64).contiguous()
         B = X.shape[0]
+        if X.shape != (B, di):
+            raise ValueError(f"expected inputs of shape [B, {di}], got {tuple(X.shape)}")
         if Y is not None:
-            diag = p["b_h"][None, :] + torch.cat((Y, X), dim=1) @ p["W_vh"]        # label rows first (:236)
-            Q = torch.diag_embed(diag)
-            if p["W_hh"] is not None:
-                Q = Q + p["W_hh"][None]
-        else:
-            n = no + h
-            upper = torch.zeros((n, n), dtype=torch.float64, device=self.device)
-            upper[:no, no:] += p["W_vh"][:no]
-            upper[:no, :no] += p["W_oo"]
-            if p["W_hh"] is not None:
-                upper[no:, no:] += p["W_hh"]
-            diag = torch.cat((p["b_o"], p["b_h"]))[None, :] + X @ torch.cat((p["W_vo"], p["W_vh"][no:]), dim=1)
-            Q = torch.diag_embed(diag) + upper[None]
-        return (Q / self.beta_eff).contiguous()
+            Y = Y.to(torch.float64).contiguous()
+            if Y.shape != (B, no):
+                raise ValueError(f"expected labels of shape [{B}, {no}], got {tuple(Y.shape)}")
+        n = h if Y is not None else no + h
+        Q = torch.empty((B, n, n), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_disc_build_qubo(self._flat.data_ptr(), di, no, h, int(self.restricted), X.data_ptr(),
+                                                 Y.data_ptr() if Y is not None else None, B, float(self.beta_eff),
+                                                 Q.data_ptr(), _s._stream_ptr(self.device))
+        _lib.check(rc)
+        return Q
 
     def create_qubo_matrix_from(self, input_vector, label=None) -> np.ndarray:
         X = torch.as_tensor(np.asarray(input_vector, dtype=np.float64)).to(self.device)[None]
@@ -191,61 +211,45 @@ class DiscQBM:
         Y = None if label is None else self._labels(np.atleast_1d(label), 1)
         return self.sample_batch(self.build_qubos(X, Y))[0].cpu().numpy()
 
-    # ---- statistics -> parameter-shaped errors (sums over the local images) -----------------------
-    def _errors(self, X, Y, mean_c, sec_c, mean_u, sec_u) -> dict:
+    # ---- statistics -> parameter-shaped errors (sums over the local images), K8 -------------------
+    def _errors(self, X, Y, mean_c, sec_c, mean_u, sec_u) -> torch.Tensor:
+        """flat float64 [param_count + 1]: (clamped - unclamped) statistics in the parameter layout + the NLL sum."""
         no, h, di = self.n_output_nodes, self.n_hidden_nodes, self.dim_input
-        Mh_c, Mh_u, Mo_u = mean_c, mean_u[:, no:], mean_u[:, :no]
-        e = {}
-        e["b_h"] = (Mh_c - Mh_u).sum(dim=0)
-        e["b_o"] = (Y - Mo_u).sum(dim=0)
-        W = torch.zeros((no + di, h), dtype=torch.float64, device=self.device)
-        W[:di] = X.T @ (Mh_c - Mh_u)              # statistics rows: x first, then the label (Q1)
-        W[di:] = Y.T @ Mh_c
-        e["W_vh"] = W
-        e["W_vo"] = X.T @ (Y - Mo_u)
-        oo = torch.triu(Y.T @ Y - sec_u[:, :no, :no].sum(dim=0), diagonal=1)
-        if self.stats_mode == "faster" and not self.restricted:
-            oo = 2.0 * oo                          # faster_dqbm.py:831-845 adds the o-o term twice (Q2)
-        e["W_oo"] = oo
-        if not self.restricted:
-            if self.stats_mode == "loop":
-                e["W_hh"] = torch.triu(sec_c.sum(dim=0) - sec_u[:, no:, no:].sum(dim=0), diagonal=1)
-            else:
-                e["W_hh"] = torch.zeros((h, h), dtype=torch.float64, device=self.device)   # never accumulated (Q2)
-        return e
+        B = X.shape[0]
+        err = torch.empty(self._flat.numel() + 1, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_disc_errors(di, no, h, int(self.restricted), int(self.stats_mode == "faster"),
+                                             X.data_ptr(), Y.data_ptr(), B, mean_c.data_ptr(),
+                                             sec_c.data_ptr() if sec_c is not None else None, mean_u.data_ptr(),
+                                             sec_u.data_ptr(), err.data_ptr(), _s._stream_ptr(self.device))
+        _lib.check(rc)
+        return err
 
     def train_for_one_iteration(self, x_batch, y_batch, learning_rate, nll=None, global_batch=None, first_image=0):
         """faster_dqbm.py:998-1064 / discriminative_qbm.py:875-951 for a whole minibatch.  With a
         process group, ``x_batch`` is this rank's shard, ``global_batch`` the minibatch size the errors
         are divided by and ``first_image`` the shard's offset.  Returns (errors_biases_output, avg loss)."""
-        X = self._to_dev(x_batch)
+        X = self._to_dev(x_batch).contiguous()
         B = X.shape[0]
-        Y = self._labels(y_batch, B)
+        Y = self._labels(y_batch, B).contiguous()
         Sc = self.sample_batch(self.build_qubos(X, Y), first_image)
         Su = self.sample_batch(self.build_qubos(X, None), first_image)
         mean_c, sec_c = _s.phase_stats(Sc, second=not self.restricted and self.stats_mode == "loop")
         mean_u, sec_u = _s.phase_stats(Su, second=True)
-        err = self._errors(X, Y, mean_c, sec_c, mean_u, sec_u)
         if self.keep_samples:
             self.last_samples = (Sc, Su)
-        if self.stats_mode == "faster":
-            # NLL of output node 0 (faster_dqbm.py:972-994), float32 like torch.tensor(output_probs)
-            p1 = mean_u[:, 0].to(torch.float32)
-            lp = torch.log(torch.stack((1 - p1, p1), dim=1) + 1e-12)
-            loss_sum = -lp.gather(1, Y[:, :1].to(torch.int64)).sum().to(torch.float64)
-        else:
-            # discriminative_qbm.py:875-951 has its NLL commented out: total_nll_loss stays 0
-            loss_sum = torch.zeros((), dtype=torch.float64, device=self.device)
-        names = [k for k in ("b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh") if k in err]
-        flat = _d.all_reduce_sum_(_d.pack([err[k] for k in names] + [loss_sum]), self.pg)
+        flat = _d.all_reduce_sum_(self._errors(X, Y, mean_c, sec_c, mean_u, sec_u), self.pg)
         gb = float(global_batch if global_batch is not None else B)
-        _d.sgd_apply_([self._p[k] for k in names], flat, learning_rate, gb)
-        pos = sum(err[k].numel() for k in names[:names.index("b_o")])
-        ebo = flat[pos:pos + err["b_o"].numel()] / gb
-        avg_loss = float(flat[-1].item() / gb)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_sgd_apply(self._flat.data_ptr(), flat.data_ptr(), self._flat.numel(), float(learning_rate), gb,
+                                           _s._stream_ptr(self.device))
+        _lib.check(rc)
+        h, no = self.n_hidden_nodes, self.n_output_nodes
+        tail = torch.cat((flat[h:h + no] / gb, flat[-1:] / gb)).cpu().numpy()       # one device -> host read per step
+        avg_loss = float(tail[-1])
         self.nll_per_batch.append(avg_loss)
         self.step_count += 1
-        return ebo.cpu().numpy(), avg_loss
+        return tail[:no], avg_loss
 
     # ---- prediction (faster_dqbm.py:1227-1241) ------------------------------------------------------
     def predict_batch(self, X) -> np.ndarray:
