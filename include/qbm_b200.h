@@ -54,6 +54,11 @@ int         qbm_device_info(int *sm_count, int *cc_major, int *cc_minor);
  */
 int qbm_qubo_to_ising(const double *Q, int n, long long batch, float *J_out, float *h_out,
                       double *offset, double *range, void *stream);
+/* Geometric beta schedule from K0's `range` output: hot = ln 2 / range[1], cold = ln 100 / range[0] (neal's legacy
+ * _default_ising_beta_range; [0.1, 1.0] when every bias is zero), then np.geomspace(hot, cold, num_betas) cast to
+ * float32.  ref: neal/sampler.py as called from src/qubo/sampler.py:31-32.
+ *   range [batch, 2] float64, betas_out [batch, num_betas] float32 */
+int qbm_beta_schedule(const double *range, long long batch, int num_betas, float *betas_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * K1  simulated-annealing sampler (one warp per read/chain).

@@ -71,7 +71,42 @@ __global__ void __launch_bounds__(WARPS * 32) qubo_to_ising_kernel(const double 
     }
 }
 
+// neal's legacy default beta range (sampler.py:281) from K0's two reductions, then
+// np.geomspace(hot, cold, num_betas) = 10 ** linspace(log10 hot, log10 cold) with pinned end points, cast to fp32
+__global__ void beta_schedule_kernel(const double *__restrict__ range, const long long batch, const int num_betas,
+                                     float *__restrict__ betas)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= batch * num_betas) return;
+    const long long q = e / num_betas;
+    const int i = (int)(e % num_betas);
+    const double mn = range[2 * q], mx = range[2 * q + 1];
+    const bool empty = mx == 0.0;                                  // no bias at all: neal falls back to [0.1, 1.0]
+    const double hot = empty ? 0.1 : 0.6931471805599453 / mx;      // np.log(2)
+    const double cold = empty ? 1.0 : 4.605170185988092 / mn;      // np.log(100)
+    double v;
+    if (i == 0) v = hot;
+    else if (i == num_betas - 1) v = cold;
+    else {
+        const double ls = log10(hot), le = log10(cold);
+        const double step = (le - ls) / (double)(num_betas - 1);
+        v = pow(10.0, (double)i * step + ls);
+    }
+    betas[e] = (float)v;
+}
+
 }  // namespace
+
+extern "C" QBM_API int qbm_beta_schedule(const double *range, long long batch, int num_betas, float *betas_out, void *stream)
+{
+    QBM_CHECK_ARG(range && betas_out, "qbm_beta_schedule: null pointer argument");
+    QBM_CHECK_ARG(batch >= 1 && num_betas >= 0, "qbm_beta_schedule: bad sizes");
+    if (num_betas == 0) return QBM_OK;
+    const long long total = batch * num_betas;
+    beta_schedule_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(range, batch, num_betas, betas_out);
+    QBM_LAUNCH_OK("beta_schedule_kernel");
+    return QBM_OK;
+}
 
 extern "C" QBM_API int qbm_qubo_to_ising(const double *Q, int n, long long batch, float *J_out, float *h_out,
                                  double *offset, double *range, void *stream)

@@ -27,33 +27,18 @@ import torch
 from . import _lib, dist as _d, ising, sampler as _s
 
 
-def geomspace_device(lo: torch.Tensor, hi: torch.Tensor, num: int) -> torch.Tensor:
-    """np.geomspace along dim 1 on the device (same formula: 10 ** linspace(log10 lo, log10 hi), end
-    points pinned), float64 [B, num]."""
-    if num == 0:
-        return torch.zeros((lo.shape[0], 0), dtype=torch.float64, device=lo.device)
-    ls, le = torch.log10(lo), torch.log10(hi)
-    if num == 1:
-        return lo[:, None].clone()
-    step = (le - ls) / (num - 1)
-    y = torch.arange(num, dtype=torch.float64, device=lo.device)[None, :] * step[:, None] + ls[:, None]
-    y[:, -1] = le
-    out = torch.pow(torch.tensor(10.0, dtype=torch.float64, device=lo.device), y)
-    out[:, 0] = lo
-    out[:, -1] = hi
-    return out
-
-
 def schedule_device(rng: torch.Tensor, num_sweeps: int):
     """Legacy neal beta range + geometric schedule from K0's ``range`` output ([B,2] = min non-zero
     |bias|, max total |bias|); all-zero problems get neal's [0.1, 1.0].  Returns (betas f32 [B,nb], spb)."""
     spb = int(max(1, num_sweeps // 1000.0))
     nb = -(-num_sweeps // spb) if num_sweeps > 0 else 0
-    mn, mx = rng[:, 0], rng[:, 1]
-    empty = mx == 0
-    hot = torch.where(empty, torch.full_like(mx, 0.1), np.log(2) / torch.where(empty, torch.ones_like(mx), mx))
-    cold = torch.where(empty, torch.ones_like(mn), np.log(100) / torch.where(empty, torch.ones_like(mn), mn))
-    return geomspace_device(hot, cold, nb).to(torch.float32), spb
+    rng = rng.contiguous()
+    B = rng.shape[0]
+    betas = torch.empty((B, nb), dtype=torch.float32, device=rng.device)
+    with torch.cuda.device(rng.device):
+        rc = _lib.load().qbm_beta_schedule(rng.data_ptr(), B, nb, betas.data_ptr(), _s._stream_ptr(rng.device))
+    _lib.check(rc)
+    return betas, spb
 
 
 class DiscQBM:
