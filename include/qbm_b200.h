@@ -203,6 +203,32 @@ int qbm_convdeep_context(const double *X, const double *kernel, long long B, int
                          int pool, double *fmap_out, int *pooled_out, double *patches_out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * K10 / K11  the Conv-Deep training step around the sampler, one launch each per minibatch (float64).
+ * Model structure: P pooled conv units, num_layers sequential layers of layer_sizes[] units (host array, at most 8),
+ * n_labels outputs; QUBO variables = [pooled | sequential layers | outputs (unclamped only)].
+ * Parameters live in ONE flat buffer, which is also the layout of the error buffer:
+ *   [ b_conv (1 when shared_bias, else absent) | b_seq | b_out | kernel (k*k) | W_seq[0..L-1] | W_intra[0..L-1]
+ *     (absent when restricted) | W_hy (last layer x n_labels) | W_oo (n_labels x n_labels) ]
+ *   qbm_convdeep_build_qubo  ref: build_unclamped_qubo / build_clamped_qubo, src/qubo/builder.py:21-110.
+ *                            fmap [B, num_conv], pooled [B, P] from qbm_convdeep_context; Y [B, n_labels] label
+ *                            vectors (clamped) or NULL (unclamped); Q_out [B, n, n] divided by beta_eff
+ *   qbm_convdeep_errors      ref: get_average_configuration_single (src/train/train.py:135-253), clamped - unclamped,
+ *                            summed over the B local images, from the moments of K3 (mean_c [B, nh], second_c
+ *                            [B, nh, nh], mean_u [B, nh+nl], second_u [B, nh+nl, nh+nl]); round_float32: round the
+ *                            moments through float32 like the reference's float32 sample matrix; labels int32 [B];
+ *                            err_out has param_count + 1 elements, the last is the loss sum of train.py:45-50
+ */
+long long qbm_convdeep_param_count(int P, int num_layers, const int *layer_sizes, int n_labels, int kernel_size,
+                                   int restricted, int shared_bias);
+int qbm_convdeep_build_qubo(const double *params, int P, int num_layers, const int *layer_sizes, int n_labels,
+                            int kernel_size, int restricted, int shared_bias, const double *fmap, int num_conv,
+                            const int *pooled, const double *Y, long long B, double beta_eff, double *Q_out, void *stream);
+int qbm_convdeep_errors(int P, int num_layers, const int *layer_sizes, int n_labels, int kernel_size, int restricted,
+                        int shared_bias, int round_float32, int one_hot, const double *patches, const double *Y,
+                        const int *labels, long long B, const double *mean_c, const double *second_c, const double *mean_u,
+                        const double *second_u, double *err_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Test hooks: run the device versions of the trajectory primitives on `count` inputs so that
  * tests can compare them bit-for-bit with the oracle's independent C restatement.
  *   qbm_test_philox: ctr [count,4] u32, key [count,2] u32 -> out [count,4] u32

@@ -52,6 +52,11 @@ SIGNATURES = {
     "qbm_sgd_apply": (_c_i, [_c_p, _c_p, _c_ll, ctypes.c_double, ctypes.c_double, _c_p]),
     "qbm_convdeep_num_pooled": (_c_i, [_c_i] * 5),
     "qbm_convdeep_context": (_c_i, [_c_p, _c_p, _c_ll, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_p]),
+    "qbm_convdeep_param_count": (_c_ll, [_c_i, _c_i, _c_p, _c_i, _c_i, _c_i, _c_i]),
+    "qbm_convdeep_build_qubo": (_c_i, [_c_p, _c_i, _c_i, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_i, _c_p, _c_p, _c_ll,
+                                       ctypes.c_double, _c_p, _c_p]),
+    "qbm_convdeep_errors": (_c_i, [_c_i, _c_i, _c_p, _c_i, _c_i, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_p, _c_ll, _c_p, _c_p,
+                                   _c_p, _c_p, _c_p, _c_p]),
     "qbm_test_philox": (_c_i, [_c_p, _c_p, _c_p, _c_ll, _c_p]),
     "qbm_test_neg_log": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
 }

@@ -18,6 +18,7 @@ and per-unit conv biases crash inside the reference and are rejected here.
 """
 from __future__ import annotations
 
+import ctypes
 import random
 
 import numpy as np
@@ -85,9 +86,35 @@ class ConvDeepQBM:
             b_conv = np.zeros(self.sequential_layer_sizes)             # the reference's placeholder (:178), never used
         b_seq = np.random.uniform(-1, 1, sum(self.sequential_layer_sizes))
         b_out = np.random.uniform(-1, 1, nl)
-        self._p = {}
-        self.set_params(kernel=kernel, W_seq=W_seq, W_intra=W_intra, W_hy=W_hy, W_oo=W_oo, b_conv=b_conv, b_seq=b_seq,
-                        b_out=b_out)
+        # trainable parameters live in ONE flat float64 device buffer (layout of include/qbm_b200.h, K10/K11);
+        # self._p holds views into it.  With hidden_bias_type "none" the reference's b_conv placeholder is not a parameter.
+        self._shared_bias = hidden_bias_type == "shared"
+        sizes = self.sequential_layer_sizes
+        widths = [P] + sizes
+        shapes = ([("b_conv", (1,))] if self._shared_bias else []) + [("b_seq", (sum(sizes),)), ("b_out", (nl,)), ("kernel", (k, k))]
+        shapes += [(("W_seq", li), (widths[li], widths[li + 1])) for li in range(len(sizes))]
+        if not self.is_restricted:
+            shapes += [(("W_intra", li), (sizes[li], sizes[li])) for li in range(len(sizes))]
+        shapes += [("W_hy", (widths[-1], nl)), ("W_oo", (nl, nl))]
+        self._sizes_c = (ctypes.c_int * max(1, len(sizes)))(*sizes)
+        total = sum(int(np.prod(sh)) for _, sh in shapes)
+        assert total == _lib.load().qbm_convdeep_param_count(P, len(sizes), self._sizes_c, nl, k, int(self.is_restricted),
+                                                             int(self._shared_bias))
+        self._flat = torch.zeros(total, dtype=torch.float64, device=self.device)
+        self._p = {"W_seq": [None] * len(sizes), "W_intra": None if self.is_restricted else [None] * len(sizes),
+                   "b_conv": None}
+        pos = 0
+        for nm, sh in shapes:
+            cnt = int(np.prod(sh))
+            view = self._flat[pos:pos + cnt].view(sh)
+            if isinstance(nm, tuple):
+                self._p[nm[0]][nm[1]] = view
+            else:
+                self._p[nm] = view
+            pos += cnt
+        self._b_conv_placeholder = None if self._shared_bias else np.asarray(b_conv, dtype=np.float64)
+        self.set_params(kernel=kernel, W_seq=W_seq, W_intra=W_intra, W_hy=W_hy, W_oo=W_oo, b_seq=b_seq, b_out=b_out,
+                        **({"b_conv": b_conv} if self._shared_bias else {}))
         self._init_cache = {}
         self.keep_samples = False
         self.last_samples = None
@@ -98,22 +125,33 @@ class ConvDeepQBM:
               "weights_output_output": "W_oo", "weights_interlayer_sequential": "W_intra", "biases_conv_units": "b_conv",
               "biases_sequential_units": "b_seq", "biases_output": "b_out"}
 
-    def _dev(self, v):
-        return torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device).clone()
+    def _copy_in(self, dst, v, name):
+        v = torch.as_tensor(np.asarray(v, dtype=np.float64)).to(self.device)
+        if v.shape != dst.shape:
+            raise ValueError(f"{name}: expected shape {tuple(dst.shape)}, got {tuple(v.shape)}")
+        dst.copy_(v)
 
     def set_params(self, **kw):
         for k, v in kw.items():
-            if v is None:
-                self._p[k] = None
-            elif isinstance(v, (list, tuple)):
-                self._p[k] = [self._dev(a) for a in v]
+            if k == "b_conv" and not self._shared_bias:
+                self._b_conv_placeholder = np.asarray(v, dtype=np.float64)
+            elif self._p.get(k) is None:
+                if v is not None:
+                    raise ValueError(f"{k} does not exist in this model (restricted / no sequential layers)")
+            elif isinstance(self._p[k], list):
+                if len(v) != len(self._p[k]):
+                    raise ValueError(f"{k}: expected {len(self._p[k])} layers")
+                for dst, a in zip(self._p[k], v):
+                    self._copy_in(dst, a, k)
             else:
-                self._p[k] = self._dev(v)
+                self._copy_in(self._p[k], v, k)
 
     def get_params(self) -> dict:
         out = {}
         for k, v in self._p.items():
             out[k] = None if v is None else ([a.cpu().numpy() for a in v] if isinstance(v, list) else v.cpu().numpy())
+        if not self._shared_bias:
+            out["b_conv"] = self._b_conv_placeholder.copy()
         return out
 
     def __getattr__(self, name):
@@ -155,40 +193,25 @@ class ConvDeepQBM:
         return fmap, pooled, patches
 
     # ---- QUBO construction (builder.py:21-110) -------------------------------------------------------
-    def _blocks(self):
-        P, sizes = self.num_pooled_units, self.sequential_layer_sizes
-        starts = [0, P]
-        for s in sizes:
-            starts.append(starts[-1] + s)
-        layers = [(starts[i], starts[i + 1]) for i in range(len(sizes) + 1)]     # [pooled, seq_1, ..., seq_k]
-        return layers, layers[-1]
+    def _struct(self):
+        return (self.num_pooled_units, len(self.sequential_layer_sizes), self._sizes_c, self.num_lable_nodes, self.kernel_size,
+                int(self.is_restricted), int(self._shared_bias))
 
     def build_qubos(self, fmap: torch.Tensor, pooled: torch.Tensor, Y: torch.Tensor | None, beta_eff: float = 1.0):
-        """float64 [B, n, n]: n = n_hidden (+ num_lable_nodes when ``Y`` is None, i.e. unclamped)."""
-        p, P, nh, nl = self._p, self.num_pooled_units, self.n_hidden, self.num_lable_nodes
+        """float64 [B, n, n] (K10): n = n_hidden (+ num_lable_nodes when ``Y`` is None, i.e. unclamped)."""
+        nh, nl = self.n_hidden, self.num_lable_nodes
         B = fmap.shape[0]
         n = nh + (nl if Y is None else 0)
-        layers, last = self._blocks()
-        upper = torch.zeros((n, n), dtype=torch.float64, device=self.device)
-        for li, W in enumerate(p["W_seq"]):
-            (ps, pe), (cs, ce) = layers[li], layers[li + 1]
-            upper[ps:pe, cs:ce] += W
-            if p["W_intra"] is not None:
-                upper[cs:ce, cs:ce] += torch.triu(p["W_intra"][li], diagonal=1)
-        diag = torch.zeros((B, n), dtype=torch.float64, device=self.device)
-        conv = fmap.gather(1, pooled.to(torch.int64))
-        if self.hidden_bias_type == "shared":
-            conv = conv + p["b_conv"][0]
-        diag[:, :P] = conv
-        if p["b_seq"].numel():
-            diag[:, P:nh] += p["b_seq"][None, :]
-        if Y is None:
-            upper[last[0]:last[1], nh:] += p["W_hy"]
-            upper[nh:, nh:] += torch.triu(p["W_oo"], diagonal=1)
-            diag[:, nh:] += p["b_out"][None, :]
-        else:
-            diag[:, last[0]:last[1]] += Y @ p["W_hy"].T                       # label bias (:106-108)
-        return ((torch.diag_embed(diag) + upper[None]) / float(beta_eff)).contiguous()
+        fmap, pooled = fmap.contiguous(), pooled.contiguous()
+        if Y is not None:
+            Y = Y.to(torch.float64).contiguous()
+        Q = torch.empty((B, n, n), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_convdeep_build_qubo(self._flat.data_ptr(), *self._struct(), fmap.data_ptr(), fmap.shape[1],
+                                                     pooled.data_ptr(), Y.data_ptr() if Y is not None else None, B,
+                                                     float(beta_eff), Q.data_ptr(), _s._stream_ptr(self.device))
+        _lib.check(rc)
+        return Q
 
     # ---- sampling (pipeline.py:20,35 -> sampler.py:26-33) -----------------------------------------------
     def _init_states(self, B, n, num_reads):
@@ -218,33 +241,18 @@ class ConvDeepQBM:
         uni = torch.full_like(out, 1.0 / out.shape[1])
         return torch.where(s > 0, out / torch.where(s > 0, s, torch.ones_like(s)), uni)
 
-    def _moments(self, S: torch.Tensor, second: bool = True):
-        mean, sec = _s.phase_stats(S, second=second)
-        if self.stats_dtype == "float32":           # the reference averages float32 samples (sampler.py:33)
-            mean = mean.to(torch.float32).to(torch.float64)
-            sec = None if sec is None else sec.to(torch.float32).to(torch.float64)
-        return mean, sec
-
-    # ---- statistics -> parameter-shaped errors, summed over the local images (train.py:135-253) ------
-    def _errors(self, patches, Ylab, mc, sc, mu, su) -> dict:
-        P, nh, nl = self.num_pooled_units, self.n_hidden, self.num_lable_nodes
-        layers, last = self._blocks()
-        e = {}
-        if self.hidden_bias_type == "shared":
-            e["b_conv"] = (mc[:, :P].sum(dim=1) - mu[:, :P].sum(dim=1)).sum().reshape(1)
-        e["b_seq"] = (mc[:, P:nh] - mu[:, P:nh]).sum(dim=0)
-        e["b_out"] = (Ylab - mu[:, nh:]).sum(dim=0)
-        e["kernel"] = torch.einsum("bpij,bp->ij", patches, mc[:, :P] - mu[:, :P])
-        e["W_seq"], e["W_intra"] = [], []
-        for li in range(len(self.sequential_layer_sizes)):
-            (ps, pe), (cs, ce) = layers[li], layers[li + 1]
-            e["W_seq"].append((sc[:, ps:pe, cs:ce] - su[:, ps:pe, cs:ce]).sum(dim=0))
-            if not self.is_restricted:
-                e["W_intra"].append(torch.triu((sc[:, cs:ce, cs:ce] - su[:, cs:ce, cs:ce]).sum(dim=0), diagonal=1))
-        ls, le = last
-        e["W_hy"] = mc[:, ls:le].T @ Ylab - su[:, ls:le, nh:].sum(dim=0)
-        e["W_oo"] = torch.triu(Ylab.T @ Ylab - su[:, nh:, nh:].sum(dim=0), diagonal=1)
-        return e
+    # ---- statistics -> parameter-shaped errors + loss, summed over the local images (train.py:135-253), K11 ------
+    def _errors(self, patches, Ylab, y, one_hot, mc, sc, mu, su) -> torch.Tensor:
+        B = patches.shape[0]
+        err = torch.empty(self._flat.numel() + 1, dtype=torch.float64, device=self.device)
+        y32 = y.to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_convdeep_errors(*self._struct(), int(self.stats_dtype == "float32"), int(bool(one_hot)),
+                                                 patches.data_ptr(), Ylab.data_ptr(), y32.data_ptr(), B, mc.data_ptr(),
+                                                 sc.data_ptr(), mu.data_ptr(), su.data_ptr(), err.data_ptr(),
+                                                 _s._stream_ptr(self.device))
+        _lib.check(rc)
+        return err
 
     def _labels(self, Y, B, one_hot):
         y = (Y if torch.is_tensor(Y) else torch.as_tensor(np.asarray(Y))).to(self.device).reshape(B).to(torch.int64)
@@ -259,25 +267,19 @@ class ConvDeepQBM:
         fmap, pooled, patches = self.prepare_context_batch(X)
         B = fmap.shape[0]
         y, Ylab = self._labels(Y, B, one_hot)
+        Ylab = Ylab.contiguous()
         Sc = self.sample_batch(self.build_qubos(fmap, pooled, Ylab, beta_eff), num_reads, first_image)
         Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads, first_image)
-        mc, sc = self._moments(Sc)
-        mu, su = self._moments(Su)
+        mc, sc = _s.phase_stats(Sc)
+        mu, su = _s.phase_stats(Su)
         if self.keep_samples:
             self.last_samples = (Sc, Su)
-        probs = self._probs(mu, one_hot)
-        py = probs.gather(1, y[:, None])[:, 0].to(torch.float64)
-        loss_sum = -torch.log(torch.clamp(py, min=1e-12)).sum()
-        err = self._errors(patches, Ylab, mc, sc, mu, su)
-        names = [k for k in ("b_conv", "b_seq", "b_out", "kernel", "W_seq", "W_intra", "W_hy", "W_oo")
-                 if k in err and not (k == "W_intra" and self.is_restricted)]
-        parts, targets = [], []
-        for k in names:
-            parts += err[k] if isinstance(err[k], list) else [err[k]]
-            targets += self._p[k] if isinstance(self._p[k], list) else [self._p[k]]
-        flat = _d.all_reduce_sum_(_d.pack(parts + [loss_sum]), self.pg)
+        flat = _d.all_reduce_sum_(self._errors(patches, Ylab, y, one_hot, mc, sc, mu, su), self.pg)
         gb = float(global_batch if global_batch is not None else B)
-        _d.sgd_apply_(targets, flat, lr, gb)
+        with torch.cuda.device(self.device):
+            rc = _lib.load().qbm_sgd_apply(self._flat.data_ptr(), flat.data_ptr(), self._flat.numel(), float(lr), gb,
+                                           _s._stream_ptr(self.device))
+        _lib.check(rc)
         self.step_count += 1
         return float(flat[-1].item() / max(1.0, gb))
 
@@ -285,5 +287,5 @@ class ConvDeepQBM:
     def predict_proba_batch(self, X, num_reads: int, beta_eff: float = 1.0, one_hot: bool = False) -> np.ndarray:
         fmap, pooled, _ = self.prepare_context_batch(X)
         Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads)
-        mu, _ = self._moments(Su, second=False)
+        mu, _ = _s.phase_stats(Su, second=False)
         return self._probs(mu, one_hot).cpu().numpy()

@@ -113,3 +113,232 @@ extern "C" QBM_API int qbm_convdeep_context(const double *X, const double *kerne
     QBM_LAUNCH_OK("convdeep_context_kernel");
     return QBM_OK;
 }
+
+// ================================================================================================
+// K10 / K11: the Conv-Deep training step around the sampler, one launch each per minibatch (float64).
+//   K10 convdeep_build_qubo  build_unclamped_qubo / build_clamped_qubo        src/qubo/builder.py:21-110
+//   K11 convdeep_errors      get_average_configuration_single, clamped - unclamped, summed over the minibatch,
+//                            + the loss of train_one_iteration                 src/train/train.py:12-253
+// Variable layout of a QUBO: [pooled conv units (P) | sequential layers | outputs (unclamped only)].
+// Parameter layout (one flat float64 buffer, also the layout of the error buffer):
+//   [ b_conv (1 when shared, else absent) | b_seq | b_out | kernel (k*k) | W_seq[0..L-1] | W_intra[0..L-1] (absent
+//     when restricted) | W_hy (last x nl) | W_oo (nl x nl) ]
+// ================================================================================================
+namespace {
+
+constexpr int CD_MAXL = 8;
+
+struct ConvDeepDims {
+    int P, L, nl, kk, restricted, shared_bias;
+    int sizes[CD_MAXL];
+    // variable index where layer li starts: li = 0 pooled, 1..L sequential, L+1 outputs
+    __host__ __device__ int start(int li) const
+    {
+        int s = 0;
+        if (li >= 1) s = P;
+        for (int i = 1; i < li; ++i) s += sizes[i - 1];
+        return s;
+    }
+    __host__ __device__ int width(int li) const { return li == 0 ? P : (li <= L ? sizes[li - 1] : nl); }
+    __host__ __device__ int nh() const { return start(L + 1); }
+    __host__ __device__ int nseq() const { return nh() - P; }
+    __host__ __device__ int layer_of(int v) const
+    {
+        int li = 0;
+        while (li <= L && v >= start(li + 1)) ++li;
+        return li;
+    }
+    __host__ __device__ long long off_bconv() const { return 0; }
+    __host__ __device__ long long off_bseq() const { return shared_bias ? 1 : 0; }
+    __host__ __device__ long long off_bout() const { return off_bseq() + nseq(); }
+    __host__ __device__ long long off_kernel() const { return off_bout() + nl; }
+    __host__ __device__ long long off_wseq(int li) const
+    {
+        long long o = off_kernel() + kk;
+        for (int i = 0; i < li; ++i) o += (long long)width(i) * width(i + 1);
+        return o;
+    }
+    __host__ __device__ long long off_wintra(int li) const
+    {
+        long long o = off_wseq(L);
+        for (int i = 0; i < li; ++i) o += (long long)sizes[i] * sizes[i];
+        return o;
+    }
+    __host__ __device__ long long off_why() const { return restricted ? off_wseq(L) : off_wintra(L); }
+    __host__ __device__ long long off_woo() const { return off_why() + (long long)width(L) * nl; }
+    __host__ __device__ long long total() const { return off_woo() + (long long)nl * nl; }
+};
+
+// one CTA per image
+__global__ void __launch_bounds__(256) convdeep_build_qubo_kernel(const double *__restrict__ Pm, const ConvDeepDims d,
+                                                                  const double *__restrict__ fmap, const int num_conv,
+                                                                  const int *__restrict__ pooled, const double *__restrict__ Y,
+                                                                  const double beta_eff, double *__restrict__ Q)
+{
+    const size_t b = blockIdx.x;
+    const bool clamped = Y != nullptr;
+    const int nh = d.nh(), n = clamped ? nh : nh + d.nl;
+    const int L = d.L, ls = d.start(L), lw = d.width(L);
+    const double *fm = fmap + b * (size_t)num_conv;
+    const int *pi = pooled + b * (size_t)d.P;
+    const double *y = clamped ? Y + b * (size_t)d.nl : nullptr;
+    double *q = Q + b * (size_t)n * (size_t)n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int r = e / n, c = e % n;
+        const int lr = d.layer_of(r), lc = d.layer_of(c);
+        double v = 0.0;
+        if (r == c) {
+            if (lr == 0) {
+                v = fm[pi[r]];
+                if (d.shared_bias) v += Pm[d.off_bconv()];
+            } else if (lr <= L) {
+                v = Pm[d.off_bseq() + (r - d.P)];
+            } else {
+                v = Pm[d.off_bout() + (r - nh)];
+            }
+            if (clamped && r >= ls && r < ls + lw) {
+                double eff = 0.0;                                   // W_hy @ label (builder.py:106-108)
+                for (int o = 0; o < d.nl; ++o) eff = fma(Pm[d.off_why() + (size_t)(r - ls) * d.nl + o], y[o], eff);
+                v += eff;
+            }
+        } else if (lc == L + 1) {
+            if (lr == L) v = Pm[d.off_why() + (size_t)(r - ls) * d.nl + (c - nh)];                   // last hidden -> outputs
+            else if (lr == L + 1 && c > r) v = Pm[d.off_woo() + (size_t)(r - nh) * d.nl + (c - nh)]; // triu(W_oo, 1)
+        } else if (lr <= L && lc == lr + 1) {
+            v = Pm[d.off_wseq(lr) + (size_t)(r - d.start(lr)) * d.width(lc) + (c - d.start(lc))];     // layer -> next layer
+        } else if (lr == lc && lr >= 1 && lr <= L && c > r && !d.restricted) {
+            const int s0 = d.start(lr), w = d.width(lr);
+            v = Pm[d.off_wintra(lr - 1) + (size_t)(r - s0) * w + (c - s0)];                           // triu(W_intra, 1)
+        }
+        q[e] = v / beta_eff;
+    }
+}
+
+// one thread per element of the error buffer (+ 1 for the loss); sums over the local images in image order
+__global__ void convdeep_errors_kernel(const ConvDeepDims d, const long long B, const int round32, const int one_hot,
+                                       const double *__restrict__ patches, const double *__restrict__ Y,
+                                       const int *__restrict__ ylab, const double *__restrict__ Mc, const double *__restrict__ Sc,
+                                       const double *__restrict__ Mu, const double *__restrict__ Su, double *__restrict__ E)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = d.total();
+    if (e > total) return;
+    const int nh = d.nh(), nu = nh + d.nl, P = d.P, nl = d.nl, L = d.L;
+    // the reference averages float32 samples (src/qubo/sampler.py:33): moments optionally rounded through float32
+    auto R = [round32](double v) { return round32 ? (double)(float)v : v; };
+    auto mc = [&](long long b, int i) { return R(Mc[b * nh + i]); };
+    auto mu = [&](long long b, int i) { return R(Mu[b * nu + i]); };
+    auto sc = [&](long long b, int i, int j) { return R(Sc[(b * nh + i) * nh + j]); };
+    auto su = [&](long long b, int i, int j) { return R(Su[(b * nu + i) * nu + j]); };
+    double s = 0.0;
+    if (e == total) {
+        // loss of the unclamped phase (src/train/pipeline.py:22-28, src/train/train.py:45-50): float32 probabilities
+        for (long long b = 0; b < B; ++b) {
+            float py;
+            if (!one_hot) {
+                double p1 = (double)(float)Mu[b * nu + nh];
+                p1 = fmin(fmax(p1, 1e-12), 1.0 - 1e-12);
+                py = ylab[b] ? (float)p1 : (float)(1.0 - p1);
+            } else {
+                float tot = 0.0f;
+                for (int o = 0; o < nl; ++o) tot += (float)Mu[b * nu + nh + o];
+                py = tot > 0.0f ? (float)Mu[b * nu + nh + ylab[b]] / tot : 1.0f / (float)nl;
+            }
+            s -= (double)logf(fmaxf(py, 1e-12f));
+        }
+    } else if (d.shared_bias && e < d.off_bseq()) {
+        for (long long b = 0; b < B; ++b)
+            for (int i = 0; i < P; ++i) s += mc(b, i) - mu(b, i);
+    } else if (e < d.off_bout()) {
+        const int j = P + (int)(e - d.off_bseq());
+        for (long long b = 0; b < B; ++b) s += mc(b, j) - mu(b, j);
+    } else if (e < d.off_kernel()) {
+        const int o = (int)(e - d.off_bout());
+        for (long long b = 0; b < B; ++b) s += Y[b * nl + o] - mu(b, nh + o);
+    } else if (e < d.off_wseq(0)) {
+        const int ij = (int)(e - d.off_kernel());
+        for (long long b = 0; b < B; ++b)
+            for (int i = 0; i < P; ++i) s = fma(patches[(b * P + i) * d.kk + ij], mc(b, i) - mu(b, i), s);
+    } else if (e < d.off_wseq(L)) {
+        int li = 0;
+        while (e >= d.off_wseq(li + 1)) ++li;
+        const long long r = e - d.off_wseq(li);
+        const int wc = d.width(li + 1);
+        const int i = d.start(li) + (int)(r / wc), j = d.start(li + 1) + (int)(r % wc);
+        for (long long b = 0; b < B; ++b) s += sc(b, i, j) - su(b, i, j);
+    } else if (e < d.off_why()) {
+        int li = 0;
+        while (e >= d.off_wintra(li + 1)) ++li;
+        const long long r = e - d.off_wintra(li);
+        const int w = d.sizes[li], s0 = d.start(li + 1);
+        const int i = (int)(r / w), j = (int)(r % w);
+        if (i < j)
+            for (long long b = 0; b < B; ++b) s += sc(b, s0 + i, s0 + j) - su(b, s0 + i, s0 + j);
+    } else if (e < d.off_woo()) {
+        const long long r = e - d.off_why();
+        const int i = d.start(L) + (int)(r / nl), o = (int)(r % nl);
+        for (long long b = 0; b < B; ++b) s += mc(b, i) * Y[b * nl + o] - su(b, i, nh + o);
+    } else {
+        const long long r = e - d.off_woo();
+        const int o = (int)(r / nl), o2 = (int)(r % nl);
+        if (o < o2)
+            for (long long b = 0; b < B; ++b) s += Y[b * nl + o] * Y[b * nl + o2] - su(b, nh + o, nh + o2);
+    }
+    E[e] = s;
+}
+
+int make_dims(const char *who, int P, int L, const int *sizes, int nl, int k, int restricted, int shared_bias, ConvDeepDims *d)
+{
+    if (P < 1 || L < 0 || L > CD_MAXL || nl < 1 || k < 1 || (L > 0 && sizes == nullptr)) {
+        qbm_set_error("%s: bad model structure (P=%d layers=%d labels=%d kernel=%d; at most %d sequential layers)", who, P, L, nl, k,
+                      CD_MAXL);
+        return QBM_EINVAL;
+    }
+    d->P = P; d->L = L; d->nl = nl; d->kk = k * k; d->restricted = restricted ? 1 : 0; d->shared_bias = shared_bias ? 1 : 0;
+    for (int i = 0; i < CD_MAXL; ++i) d->sizes[i] = i < L ? sizes[i] : 0;
+    for (int i = 0; i < L; ++i)
+        if (sizes[i] < 1) { qbm_set_error("%s: sequential layer %d has size %d", who, i, sizes[i]); return QBM_EINVAL; }
+    return QBM_OK;
+}
+
+}  // namespace
+
+extern "C" QBM_API long long qbm_convdeep_param_count(int P, int num_layers, const int *layer_sizes, int n_labels, int kernel_size,
+                                                      int restricted, int shared_bias)
+{
+    ConvDeepDims d;
+    if (make_dims("qbm_convdeep_param_count", P, num_layers, layer_sizes, n_labels, kernel_size, restricted, shared_bias, &d)) return 0;
+    return d.total();
+}
+
+extern "C" QBM_API int qbm_convdeep_build_qubo(const double *params, int P, int num_layers, const int *layer_sizes, int n_labels,
+                                               int kernel_size, int restricted, int shared_bias, const double *fmap, int num_conv,
+                                               const int *pooled, const double *Y, long long B, double beta_eff, double *Q_out,
+                                               void *stream)
+{
+    ConvDeepDims d;
+    if (int rc = make_dims("qbm_convdeep_build_qubo", P, num_layers, layer_sizes, n_labels, kernel_size, restricted, shared_bias, &d))
+        return rc;
+    QBM_CHECK_ARG(params && fmap && pooled && Q_out, "qbm_convdeep_build_qubo: null pointer argument");
+    QBM_CHECK_ARG(B >= 1 && B <= 0x7fffffffLL && num_conv >= P, "qbm_convdeep_build_qubo: bad sizes");
+    QBM_CHECK_ARG(beta_eff != 0.0, "qbm_convdeep_build_qubo: beta_eff must not be 0");
+    convdeep_build_qubo_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(params, d, fmap, num_conv, pooled, Y, beta_eff, Q_out);
+    QBM_LAUNCH_OK("convdeep_build_qubo_kernel");
+    return QBM_OK;
+}
+
+extern "C" QBM_API int qbm_convdeep_errors(int P, int num_layers, const int *layer_sizes, int n_labels, int kernel_size, int restricted,
+                                           int shared_bias, int round_float32, int one_hot, const double *patches, const double *Y,
+                                           const int *labels, long long B, const double *mean_c, const double *second_c,
+                                           const double *mean_u, const double *second_u, double *err_out, void *stream)
+{
+    ConvDeepDims d;
+    if (int rc = make_dims("qbm_convdeep_errors", P, num_layers, layer_sizes, n_labels, kernel_size, restricted, shared_bias, &d)) return rc;
+    QBM_CHECK_ARG(patches && Y && labels && mean_c && second_c && mean_u && second_u && err_out, "qbm_convdeep_errors: null pointer argument");
+    QBM_CHECK_ARG(B >= 1, "qbm_convdeep_errors: bad batch size");
+    const long long total = d.total() + 1;
+    convdeep_errors_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        d, B, round_float32 ? 1 : 0, one_hot ? 1 : 0, patches, Y, labels, mean_c, second_c, mean_u, second_u, err_out);
+    QBM_LAUNCH_OK("convdeep_errors_kernel");
+    return QBM_OK;
+}
