@@ -31,10 +31,10 @@ def qubo_to_ising(Q: np.ndarray):
     Bm = Q + np.transpose(Q, (0, 2, 1))
     idx = np.arange(n)
     Bm[:, idx, idx] = 0.0
-    J = Bm / 4.0
     h = a / 2.0 + Bm.sum(axis=2) / 4.0
     offset = a.sum(axis=1) / 2.0 + Bm.sum(axis=(1, 2)) / 8.0
-    return h, J, offset
+    Bm /= 4.0                      # J = b / 4 in place (the sums above are taken before the scaling, as before)
+    return h, Bm, offset
 
 
 def is_linear_only(Q: np.ndarray) -> np.ndarray:
@@ -57,10 +57,11 @@ def default_beta_range(h: np.ndarray, J: np.ndarray) -> np.ndarray:
     absh = np.abs(h)
     absJ = np.abs(J)
     big = np.inf
-    min_h = np.where(absh != 0, absh, big).min(axis=1)
-    min_j = np.where(absJ != 0, absJ, big).min(axis=(1, 2))
-    min_delta = np.minimum(min_h, min_j)
     max_delta = (absh + absJ.sum(axis=2)).max(axis=1)
+    min_h = np.where(absh != 0, absh, big).min(axis=1)
+    absJ[absJ == 0.0] = big        # in place: absJ is a private temporary
+    min_j = absJ.min(axis=(1, 2))
+    min_delta = np.minimum(min_h, min_j)
     out = np.empty((h.shape[0], 2), dtype=np.float64)
     empty = ~np.isfinite(min_delta)
     with np.errstate(divide="ignore"):
