@@ -49,8 +49,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     if (!live) cl = p.total_chains - 1;           // idle warps shadow the last chain (they keep the barriers matched)
     const long long q = cl / p.num_reads;
     const int n = p.n;
-    const int ld = p.ld;
-    const float *__restrict__ J = p.Jp + (size_t)q * (size_t)n * (size_t)ld;
+    constexpr int ld = NW * 128;                  // rows are padded to whole windows of this instantiation (sa_ld)
+    // this lane's float4 column of row 0; a row is reached with a 32-bit element offset (n * ld <= 2^22)
+    const float *__restrict__ J = p.Jp + (size_t)q * (size_t)n * (size_t)ld + lane * 4;
     const float *__restrict__ hq = p.hp + (size_t)q * (size_t)ld;
     const float *__restrict__ betas = p.beta + q * p.beta_stride;
     // flag bit 1: key the stream by the read index only, so every problem of the batch sees the same
@@ -58,7 +59,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     const unsigned long long chain = p.chain_offset + (unsigned long long)((p.flags & 2u) ? (cl - q * p.num_reads) : cl);
     const uint32_t c_lo = (uint32_t)chain, c_hi = (uint32_t)(chain >> 32);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-    const bool rendezvous = (p.flags & 1u) == 0;
+    // the per-window rendezvous keeps concurrently annealed chains on the same coupling rows while those are in L1;
+    // a problem of up to two windows (<= 256 KB of couplings) stays L1/L2-resident anyway and the barrier only costs
+    const bool rendezvous = (p.flags & 1u) == 0 && NW >= 3;
     const int nw_rt = (n + 127) >> 7;             // windows actually populated (<= NW)
 
     float F[NW][4];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
             const int jend = min(32, n - jbase);
             for (int jj = 0; jj < jend; ++jj) {
                 const float sj = ((wd[k] >> jj) & 1u) ? 1.0f : -1.0f;
-                row_update<NW>(F, J + (size_t)(jbase + jj) * (size_t)ld + lane * 4, sj);
+                row_update<NW>(F, J + (uint32_t)(jbase + jj) * (uint32_t)ld, sj);
             }
         }
     }
@@ -132,7 +135,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
                         if (!have_rng) {
                             const bool pend = (dE > 0.0f) && (dE < thr);
                             if (__ballot_sync(FULL, pend) & todo) {
-                                const Philox4 o = philox4x32_10(c_lo, c_hi, t, (uint32_t)(w * 32 + lane), k0, k1);
+                                // keep the draw inside the branch: without the barrier the compiler speculates the (pure)
+                                // Philox + log above it and every cold sweep pays ~140 instructions per window for nothing
+                                uint32_t tt = t;
+                                asm volatile("" : "+r"(tt));
+                                const Philox4 o = philox4x32_10(c_lo, c_hi, tt, (uint32_t)(w * 32 + lane), k0, k1);
                                 const uint32_t u[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                                 for (int q4 = 0; q4 < KS; ++q4) bnd[q4] = fminf(thr, __fdiv_rn(neg_log_u32(u[q4]), beta));
@@ -146,7 +153,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
                         const float c = ((upm >> a) & 1u) ? -2.0f : 2.0f;     // -2 * s_a(old)
                         upm ^= 1u << a;
                         if (lane == a) sgn = -sgn;
-                        const float *row = J + (size_t)(vbase + a) * (size_t)ld + lane * 4;
+                        const float *row = J + (uint32_t)(vbase + a) * (uint32_t)ld;
                         if (NW > 1) {
                             const float4 r = __ldg(reinterpret_cast<const float4 *>(row + w * 128));
                             Fc[0] = __fmaf_rn(c, r.x, Fc[0]);
@@ -208,6 +215,10 @@ int launch_sa(const SaParams &p, cudaStream_t st)
     if (blocks > 0x7fffffffLL) {
         qbm_set_error("qbm_sa_sample: too many chains for one launch (%lld)", p.total_chains);
         return QBM_EUNSUPPORTED;
+    }
+    if (p.ld != NW * 128) {
+        qbm_set_error("qbm_sa_sample: internal error: row stride %d does not match the kernel variant (%d)", p.ld, NW * 128);
+        return QBM_EINVAL;
     }
     kern<<<(unsigned)blocks, WPC * 32, 0, st>>>(p);
     QBM_LAUNCH_OK("sa_kernel");

@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_multi_kernel(const SaParams
                                 if (!have_rng[t]) {
                                     const bool pend = (dE > 0.0f) && (dE < thr);
                                     if (__ballot_sync(FULL, pend) & todo[t]) {
-                                        const Philox4 o = philox4x32_10(c_lo[t], c_hi[t], ts, (uint32_t)(w * 32 + lane), k0, k1);
+                                        uint32_t tt = ts;
+                                        asm volatile("" : "+r"(tt));        // no speculative hoisting of the draw (see sa_kernel.cu)
+                                        const Philox4 o = philox4x32_10(c_lo[t], c_hi[t], tt, (uint32_t)(w * 32 + lane), k0, k1);
                                         bnd[t][0] = fminf(thr, __fdiv_rn(neg_log_u32(o.x), beta));
                                         bnd[t][1] = fminf(thr, __fdiv_rn(neg_log_u32(o.y), beta));
                                         bnd[t][2] = fminf(thr, __fdiv_rn(neg_log_u32(o.z), beta));
