@@ -91,26 +91,36 @@ __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__
     }
 }
 
-// class-weight / hidden-bias gradients of the discriminative step and their SGD update (:88-99,120-136)
-__global__ void rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U, long long ldu,
-                                       float *__restrict__ b_h, const float *__restrict__ P, long long ldp,
-                                       const int *__restrict__ y, const float *__restrict__ Dt, long long lddt,
-                                       int B, int H, float scale, float sparse)
+// class-weight / hidden-bias gradients of the discriminative step and their SGD update (:88-99,120-136).
+// Block = 32 hidden units x 8 batch slices; the slices are combined in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U,
+                                                             long long ldu, float *__restrict__ b_h, const float *__restrict__ P,
+                                                             long long ldp, const int *__restrict__ y, const float *__restrict__ Dt,
+                                                             long long lddt, int B, int H, float scale, float sparse)
 {
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float red[2][8][33];
+    const int hx = threadIdx.x & 31, sy = threadIdx.x >> 5;
+    const int h = blockIdx.x * 32 + hx;
     const int c = blockIdx.y;
-    if (h >= H) return;
-    const float u = U[(size_t)c * ldu + h];
-    float g = 0.0f;
-    for (int b = 0; b < B; ++b) {
-        const float o = sigm(A[(size_t)b * lda + h] + u);
-        g += (y[b] == c ? o : 0.0f) - P[(size_t)b * ldp + c] * o;
+    const bool ok = h < H;
+    const float u = ok ? U[(size_t)c * ldu + h] : 0.0f;
+    float g = 0.0f, gb = 0.0f;
+    if (ok) {
+        for (int b = sy; b < B; b += 8) {
+            const float o = sigm(A[(size_t)b * lda + h] + u);
+            g += (y[b] == c ? o : 0.0f) - P[(size_t)b * ldp + c] * o;
+            if (c == 0) gb += Dt[(size_t)h * lddt + b];
+        }
     }
-    U[(size_t)c * ldu + h] = u + scale * g;
-    if (c == 0) {
-        float gb = 0.0f;
-        for (int b = 0; b < B; ++b) gb += Dt[(size_t)h * lddt + b];
-        b_h[h] = b_h[h] + scale * gb - sparse;
+    red[0][sy][hx] = g;
+    red[1][sy][hx] = gb;
+    __syncthreads();
+    if (sy == 0 && ok) {
+        float gs = 0.0f, gbs = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gs += red[0][k][hx]; gbs += red[1][k][hx]; }
+        U[(size_t)c * ldu + h] = u + scale * gs;
+        if (c == 0) b_h[h] = b_h[h] + scale * gbs - sparse;
     }
 }
 
@@ -187,34 +197,58 @@ __global__ void __launch_bounds__(128) rbm_class_kernel(const float *__restrict_
     }
 }
 
-// CD-1 gradients of the small parameters from transposed activations ([., B] rows are contiguous over b)
-__global__ void rbm_cd_small_update_kernel(const float *__restrict__ v0t, const float *__restrict__ v1t, long long ldvt,
-                                           const float *__restrict__ p0t, const float *__restrict__ p1t, long long ldpt,
-                                           const int *__restrict__ y0, const int *__restrict__ y1, float *__restrict__ U,
-                                           long long ldu, float *__restrict__ b_v, float *__restrict__ b_h,
-                                           float *__restrict__ b_c, int B, int V, int H, int C, float scale, float sparse)
+// CD-1 gradients of the small parameters from transposed activations ([., B] rows are contiguous over b):
+// one warp per visible / hidden unit, lanes stride over the batch (coalesced), shuffle reduction.
+__device__ __forceinline__ float warp_sum(float v)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *__restrict__ v0t, const float *__restrict__ v1t,
+                                                                 long long ldvt, const float *__restrict__ p0t,
+                                                                 const float *__restrict__ p1t, long long ldpt,
+                                                                 const int *__restrict__ y0, const int *__restrict__ y1,
+                                                                 float *__restrict__ U, long long ldu, float *__restrict__ b_v,
+                                                                 float *__restrict__ b_h, float *__restrict__ b_c, int B, int V,
+                                                                 int H, int C, float scale, float sparse)
+{
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i < V) {
         float g = 0.0f;
-        for (int b = 0; b < B; ++b) g += v0t[(size_t)i * ldvt + b] - v1t[(size_t)i * ldvt + b];
-        b_v[i] = b_v[i] + scale * g - sparse;
+        for (int b = lane; b < B; b += 32) g += v0t[(size_t)i * ldvt + b] - v1t[(size_t)i * ldvt + b];
+        g = warp_sum(g);
+        if (lane == 0) b_v[i] = b_v[i] + scale * g - sparse;
     }
     if (i < H) {
-        float g = 0.0f;
-        for (int b = 0; b < B; ++b) g += p0t[(size_t)i * ldpt + b] - p1t[(size_t)i * ldpt + b];
-        b_h[i] = b_h[i] + scale * g - sparse;
-        for (int c = 0; c < C; ++c) {
-            float gu = 0.0f;
-            for (int b = 0; b < B; ++b)
-                gu += (y0[b] == c ? p0t[(size_t)i * ldpt + b] : 0.0f) - (y1[b] == c ? p1t[(size_t)i * ldpt + b] : 0.0f);
-            U[(size_t)c * ldu + i] += scale * gu;
+        float gh = 0.0f, gu[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) gu[c] = 0.0f;
+        for (int b = lane; b < B; b += 32) {
+            const float a0 = p0t[(size_t)i * ldpt + b], a1 = p1t[(size_t)i * ldpt + b];
+            const int c0 = y0[b], c1 = y1[b];
+            gh += a0 - a1;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c)
+                if (c < C) gu[c] += (c0 == c ? a0 : 0.0f) - (c1 == c ? a1 : 0.0f);
+        }
+        gh = warp_sum(gh);
+        if (lane == 0) b_h[i] = b_h[i] + scale * gh - sparse;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            if (c < C) {
+                const float t = warp_sum(gu[c]);
+                if (lane == 0) U[(size_t)c * ldu + i] += scale * t;
+            }
         }
     }
     if (i < C) {
         float g = 0.0f;
-        for (int b = 0; b < B; ++b) g += (y0[b] == i ? 1.0f : 0.0f) - (y1[b] == i ? 1.0f : 0.0f);
-        b_c[i] = b_c[i] + scale * g - sparse;
+        for (int b = lane; b < B; b += 32) g += (y0[b] == i ? 1.0f : 0.0f) - (y1[b] == i ? 1.0f : 0.0f);
+        g = warp_sum(g);
+        if (lane == 0) b_c[i] = b_c[i] + scale * g - sparse;
     }
 }
 
@@ -342,7 +376,7 @@ extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b
     QBM_LAUNCH_OK("rbm_rows_kernel");
     if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
     // class weights / hidden bias (reads the pre-update A, U), then class bias, loss, argmax
-    rbm_disc_update_kernel<<<dim3((H + 127) / 128, C), 128, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
+    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
                                                                    sparse_constant);
     QBM_LAUNCH_OK("rbm_disc_update_kernel");
     rbm_disc_finish_kernel<<<1, 256, 0, st>>>(b_c, b_v, probs, lC, y, B, C, V, scale, sparse_constant, pred, loss, 1);
@@ -386,8 +420,8 @@ extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_
     if (int rc = qbm_gemm_tf32_launch(w.v1, lV, Wt, lV, B, H, V, e3, st)) return rc;
     if (int rc = transpose(v0, lV, w.xt, lB, B, V, st)) return rc;
     // small parameters, then W += scale (v0^T ph0 - v1^T ph1) fused into two GEMM epilogues, then W^T
-    const int mx = V > H ? V : H;
-    rbm_cd_small_update_kernel<<<(mx + 127) / 128, 128, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, U, lH, b_v, b_h,
+    const int mx = (V > H ? V : H) > C ? (V > H ? V : H) : C;
+    rbm_cd_small_update_kernel<<<(mx + 7) / 8, 256, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, U, lH, b_v, b_h,
                                                                 b_c, B, V, H, C, scale, sparse_constant);
     QBM_LAUNCH_OK("rbm_cd_small_update_kernel");
     EpiParams g1 = {};
