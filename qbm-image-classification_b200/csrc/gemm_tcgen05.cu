@@ -15,13 +15,14 @@
 namespace {
 
 constexpr int BM = 128;          // rows of A per CTA  (= UMMA M, TMEM lanes)
-constexpr int BN = 128;          // rows of B per CTA  (= UMMA N, TMEM columns)
+// BN = rows of B per CTA (= UMMA N, TMEM columns) is a template parameter: 128, or 256 for problems large enough
+// to fill the 148 SMs with 128 x 256 tiles (twice the MMA work per byte staged)
 constexpr int BK = 32;           // K elements per stage: 32 x 4 B = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // K per tcgen05.mma for tf32 (32 bytes)
 constexpr int STAGES = 4;
-constexpr int TILE_BYTES = BM * BK * 4;                       // 16 KB per operand per stage
-constexpr int SMEM_BYTES = STAGES * 2 * TILE_BYTES + 1024;    // + slack for 1024-byte alignment
-constexpr int TMEM_COLS = 128;
+constexpr int A_TILE_BYTES = BM * BK * 4;                     // 16 KB per stage
+template <int BN> __host__ __device__ constexpr int stage_bytes() { return A_TILE_BYTES + BN * BK * 4; }
+template <int BN> __host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<BN>() + 1024; }   // + slack for 1024-byte alignment
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,9 +64,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr)
     return d;
 }
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+template <int BN> __host__ __device__ constexpr uint32_t idesc()
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t IDESC, uint32_t accumulate)
 {
     asm volatile(
         "{\n\t"
@@ -81,6 +85,7 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+template <int BN>
 __global__ void __launch_bounds__(128, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                  int M, int N, int K)
@@ -103,7 +108,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
     }
     if (warp == 2) {   // one warp owns the TMEM allocation
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -117,9 +122,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int s = kb % STAGES;
             const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
             mbar_wait(&empty_bar[s], ph ^ 1u);                    // slot free (passes on the first lap)
-            mbar_expect_tx(&full_bar[s], 2 * TILE_BYTES);         // OOB parts of a box are zero-filled and counted
-            tma_load_2d(smem + (size_t)s * 2 * TILE_BYTES, &tmA, kb * BK, m0, &full_bar[s]);
-            tma_load_2d(smem + (size_t)s * 2 * TILE_BYTES + TILE_BYTES, &tmB, kb * BK, n0, &full_bar[s]);
+            mbar_expect_tx(&full_bar[s], stage_bytes<BN>());      // OOB parts of a box are zero-filled and counted
+            tma_load_2d(smem + (size_t)s * stage_bytes<BN>(), &tmA, kb * BK, m0, &full_bar[s]);
+            tma_load_2d(smem + (size_t)s * stage_bytes<BN>() + A_TILE_BYTES, &tmB, kb * BK, n0, &full_bar[s]);
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer ----
@@ -128,13 +133,13 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
             mbar_wait(&full_bar[s], ph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(smem + (size_t)s * 2 * TILE_BYTES);
-            const uint32_t b_addr = a_addr + TILE_BYTES;
+            const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes<BN>());
+            const uint32_t b_addr = a_addr + A_TILE_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
                 const uint64_t ad = umma_desc_sw128(a_addr + k * UMMA_K * 4);
                 const uint64_t bd = umma_desc_sw128(b_addr + k * UMMA_K * 4);
-                umma_tf32(tmem_base, ad, bd, (kb | k) != 0 ? 1u : 0u);
+                umma_tf32(tmem_base, ad, bd, idesc<BN>(), (kb | k) != 0 ? 1u : 0u);
             }
             umma_commit(&empty_bar[s]);                           // frees the smem slot when these MMAs retire
         }
@@ -149,6 +154,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool row_ok = m < M;
     const float *tabrow = (ep.rowtab != nullptr && row_ok) ? ep.rowtab + (size_t)ep.ridx[m] * ep.ldtab : nullptr;
     const uint32_t k0 = (uint32_t)ep.seed, k1 = (uint32_t)(ep.seed >> 32);
+    const bool vecc = ep.C != nullptr && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
+    const bool vecs = ep.S != nullptr && (ep.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.S) & 15) == 0;
+    const bool vecin = ep.Cin != nullptr && (ep.ldcin & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.Cin) & 15) == 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -171,25 +179,60 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (ep.S != nullptr || ep.St != nullptr)
                 u4 = philox4x32_10((uint32_t)m, (uint32_t)((nb >> 2) + j4), ep.stream, 0x52424Du, k0, k1);
             const uint32_t us[4] = {u4.x, u4.y, u4.z, u4.w};
+            // a lane owns 4 consecutive columns of its row here: the row-major outputs (C, S) and Cin move as one
+            // 16-byte access per lane when the addresses allow it (rows of a warp are ld apart, so a 4-byte store per
+            // lane would touch one sector per element); the transposed outputs are coalesced across lanes as they are
+            const int nq = nb + j4 * 4;
+            const bool full4 = row_ok && (nq + 3 < N);
+            float cin4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (ep.Cin != nullptr && row_ok) {
+                if (full4 && vecin) {
+                    const float4 t4 = *reinterpret_cast<const float4 *>(ep.Cin + (size_t)m * ep.ldcin + nq);
+                    cin4[0] = t4.x; cin4[1] = t4.y; cin4[2] = t4.z; cin4[3] = t4.w;
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        if (nq + jj < N) cin4[jj] = ep.Cin[(size_t)m * ep.ldcin + nq + jj];
+                }
+            }
+            float v4[4], s4v[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
-                const int j = j4 * 4 + jj;
-                const int n = nb + j;
-                if (n >= N) continue;
-                float v = ep.alpha * __uint_as_float(r[j]);
-                if (ep.bias_n != nullptr) v += __ldg(ep.bias_n + n);
-                if (tabrow != nullptr) v += __ldg(tabrow + n);
+                const int n = nq + jj;
+                float v = ep.alpha * __uint_as_float(r[j4 * 4 + jj]);
+                if (n < N) {
+                    if (ep.bias_n != nullptr) v += __ldg(ep.bias_n + n);
+                    if (tabrow != nullptr) v += __ldg(tabrow + n);
+                }
                 if (ep.act == 1) v = sigmoidf_(v);
-                if (row_ok) {
-                    if (ep.Cin != nullptr) v += ep.beta * ep.Cin[(size_t)m * ep.ldcin + n];
-                    if (ep.C != nullptr) ep.C[(size_t)m * ep.ldc + n] = v;
-                    if (ep.Ct != nullptr) ep.Ct[(size_t)n * ep.ldct + m] = v;
-                    if (ep.S != nullptr || ep.St != nullptr) {
-                        // u in [0,1) with 24 bits; sample = 1 with probability v
-                        const float s = ((float)(us[jj] >> 8) * 5.9604644775390625e-8f < v) ? 1.0f : 0.0f;
-                        if (ep.S != nullptr) ep.S[(size_t)m * ep.lds + n] = s;
-                        if (ep.St != nullptr) ep.St[(size_t)n * ep.ldst + m] = s;
+                if (ep.Cin != nullptr) v += ep.beta * cin4[jj];
+                v4[jj] = v;
+                // u in [0,1) with 24 bits; sample = 1 with probability v
+                s4v[jj] = ((float)(us[jj] >> 8) * 5.9604644775390625e-8f < v) ? 1.0f : 0.0f;
+            }
+            if (row_ok) {
+                if (ep.C != nullptr) {
+                    if (full4 && vecc) *reinterpret_cast<float4 *>(ep.C + (size_t)m * ep.ldc + nq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                    else {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (nq + jj < N) ep.C[(size_t)m * ep.ldc + nq + jj] = v4[jj];
                     }
+                }
+                if (ep.S != nullptr) {
+                    if (full4 && vecs) *reinterpret_cast<float4 *>(ep.S + (size_t)m * ep.lds + nq) = make_float4(s4v[0], s4v[1], s4v[2], s4v[3]);
+                    else {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (nq + jj < N) ep.S[(size_t)m * ep.lds + nq + jj] = s4v[jj];
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int n = nq + jj;
+                    if (n >= N) continue;
+                    if (ep.Ct != nullptr) ep.Ct[(size_t)n * ep.ldct + m] = v4[jj];
+                    if (ep.St != nullptr) ep.St[(size_t)n * ep.ldst + m] = s4v[jj];
                 }
             }
         }
@@ -197,7 +240,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
 }
 
 // ---- host: tensor maps through the driver entry point (no link-time dependency on libcuda) ----
@@ -251,18 +294,27 @@ int qbm_gemm_tf32_launch(const float *A, long long lda, const float *B, long lon
     QBM_CHECK_ARG(lda >= K && ldb >= K && lda % 4 == 0 && ldb % 4 == 0,
                   "qbm_gemm_tf32: leading dimensions must be >= K and multiples of 4 floats (TMA needs 16-byte row strides)");
     QBM_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "qbm_gemm_tf32: operands must be 16-byte aligned");
+    // 128 x 256 tiles when they alone give every SM a CTA, else 128 x 128
+    const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
+    const bool wide = tiles256 >= 148;
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, B, N, K, ldb, BN);
+    rc = make_map(&tmB, B, N, K, ldb, wide ? 256 : 128);
     if (rc) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
+        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
         attr_set = true;
     }
-    dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM));
-    gemm_tf32_kernel<<<grid, 128, SMEM_BYTES, st>>>(tmA, tmB, ep, M, N, K);
+    if (wide) {
+        dim3 grid((unsigned)((N + 255) / 256), (unsigned)((M + BM - 1) / BM));
+        gemm_tf32_kernel<256><<<grid, 128, smem_bytes<256>(), st>>>(tmA, tmB, ep, M, N, K);
+    } else {
+        dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + BM - 1) / BM));
+        gemm_tf32_kernel<128><<<grid, 128, smem_bytes<128>(), st>>>(tmA, tmB, ep, M, N, K);
+    }
     QBM_LAUNCH_OK("gemm_tf32_kernel");
     return QBM_OK;
 }
