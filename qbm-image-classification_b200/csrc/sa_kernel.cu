@@ -136,9 +136,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
                             const bool pend = (dE > 0.0f) && (dE < thr);
                             if (__ballot_sync(FULL, pend) & todo) {
                                 // keep the draw inside the branch: without the barrier the compiler speculates the (pure)
-                                // Philox + log above it and every cold sweep pays ~140 instructions per window for nothing
+                                // Philox + log above it and every cold sweep pays ~140 instructions per window for nothing.
+                                // Measured per instantiation: +7..20 % for NW <= 2 and NW >= 8, -5..12 % for NW = 3..5
+                                // (where the hoisted draw overlaps load latency), neutral at NW = 6.
                                 uint32_t tt = t;
-                                asm volatile("" : "+r"(tt));
+                                if (NW <= 2 || NW >= 6) asm volatile("" : "+r"(tt));
                                 const Philox4 o = philox4x32_10(c_lo, c_hi, tt, (uint32_t)(w * 32 + lane), k0, k1);
                                 const uint32_t u[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
