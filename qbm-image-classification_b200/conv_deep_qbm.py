@@ -19,6 +19,7 @@ and per-unit conv biases crash inside the reference and are rejected here.
 from __future__ import annotations
 
 import ctypes
+import pickle
 import random
 
 import numpy as np
@@ -289,3 +290,27 @@ class ConvDeepQBM:
         Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads)
         mu, _ = _s.phase_stats(Su, second=False)
         return self._probs(mu, one_hot).cpu().numpy()
+
+    # ---- epoch loop (src/train/train.py:256-289) and checkpoints (src/model/model_ab.py:33-35) ----------------------
+    def train_model(self, train_x, train_y, batch_size, epochs, lr, sample_count, beta_eff, one_hot: bool = False):
+        """``train_model(model, ...)`` of the reference as a method: returns the running average loss after every
+        minibatch (``epoch_loss_list``)."""
+        n = len(train_x)
+        epoch_loss_list = []
+        for _ in range(1, epochs + 1):
+            epoch_loss = 0.0
+            for idx, b in enumerate(range(0, n, batch_size)):
+                loss = self.train_one_iteration(train_x[b:b + batch_size], train_y[b:b + batch_size], sample_count, beta_eff, lr,
+                                                one_hot=one_hot)
+                epoch_loss += loss
+                epoch_loss_list.append(epoch_loss / (idx + 1))
+        return epoch_loss_list
+
+    def save_weights(self, title, path=""):
+        with open(f"{path}/{title}.pkl", "wb") as f:
+            pickle.dump(self.weight_objects, f)
+
+
+def train_model(model: ConvDeepQBM, train_x, train_y, batch_size, epochs, lr, sample_count, beta_eff, one_hot: bool = False):
+    """Call-compatible with ``src/train/train.py::train_model`` for a :class:`ConvDeepQBM`."""
+    return model.train_model(train_x, train_y, batch_size, epochs, lr, sample_count, beta_eff, one_hot)

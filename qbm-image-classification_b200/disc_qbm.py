@@ -19,6 +19,8 @@ all on the current CUDA stream without a host synchronisation until the loss is 
 """
 from __future__ import annotations
 
+import os
+import pickle
 import random
 
 import numpy as np
@@ -253,3 +255,58 @@ class DiscQBM:
         if self.use_one_hot_encoding:
             return int(np.argmax(avg)), out.tolist()
         return int(np.round(avg).astype(int)[0]), out.flatten()
+
+    # ---- checkpoints: the reference's pickle format (faster_dqbm.py:1069-1077, 169-190) --------------------------
+    def save_weights(self, title, path="out"):
+        """pickle of ``weight_objects`` = [W_vh, W_vo, b_h, b_o, W_oo, W_hh] as float64 numpy arrays."""
+        with open(f"{path}/{title}.pkl", "wb") as f:
+            pickle.dump(self.weight_objects, f)
+
+    def load_savepoint(self, savepoint):
+        """Reads a weight pickle written by the reference or by :meth:`save_weights` (5 entries: semi-restricted
+        runs without W_hh; 6 entries: fully connected)."""
+        if not os.path.exists(savepoint):
+            raise FileNotFoundError("Savepoint file not found")
+        with open(savepoint, "rb") as f:
+            loaded = pickle.load(f)
+        assert len(loaded) in [5, 6]
+        names = ["W_vh", "W_vo", "b_h", "b_o", "W_oo", "W_hh"][:len(loaded)]
+        self.set_params(**{k: v for k, v in zip(names, loaded) if not (k == "W_hh" and (v is None or self.restricted))})
+
+    # ---- epoch loop (faster_dqbm.py:1079-1166) ------------------------------------------------------------------
+    def train_model(self, train_X, train_Y, val_X, val_Y, batch_size=8, learning_rate=0.005):
+        """Same loop as the reference: minibatches in order (a shorter last batch included), weights pickled after
+        every epoch when ``speicherort`` is set, validation accuracy per epoch -- with the validation set predicted in
+        ONE batched launch instead of one sampler call per image.  Returns the history dict."""
+        save_folder = None
+        if self.speicherort is not None:
+            save_folder = str(self.speicherort) + str(self.param_string)
+            os.makedirs(save_folder, exist_ok=True)
+        hist = {"errors_per_batch": [], "error_per_epoch": [], "nll_per_epoch": [], "acc_per_epoch": [], "auc_per_epoch": []}
+        train_X, train_Y = np.asarray(train_X), np.asarray(train_Y)
+        val_Y = np.asarray(val_Y)
+        num_batches = max(1, len(train_X) // batch_size)
+        for epoch in range(1, self.epochs + 1):
+            epoch_errors, epoch_nll = 0.0, 0.0
+            for b in range(0, len(train_X), batch_size):
+                xb, yb = train_X[b:b + batch_size], train_Y[b:b + batch_size]
+                if len(xb) == 0:
+                    continue
+                ebo, nll = self.train_for_one_iteration(xb, yb, learning_rate)
+                hist["errors_per_batch"].append(float(np.mean(ebo)))
+                epoch_errors += float(np.mean(ebo))
+                epoch_nll += nll
+            if save_folder is not None:
+                self.save_weights(f"e{epoch}_{self.param_string}", save_folder)
+            pred = self.predict_batch(val_X)
+            truth = val_Y.argmax(axis=1) if val_Y.ndim == 2 and val_Y.shape[1] > 1 else val_Y.reshape(-1).astype(int)
+            hist["acc_per_epoch"].append(float(np.mean(pred == truth)))
+            try:
+                from sklearn.metrics import roc_auc_score
+                hist["auc_per_epoch"].append(float(roc_auc_score(truth, pred)) if len(np.unique(truth)) == 2 else float("nan"))
+            except Exception:                                 # AUC is reporting only (src/metrics.py is out of scope)
+                hist["auc_per_epoch"].append(float("nan"))
+            hist["error_per_epoch"].append(epoch_errors / num_batches)
+            hist["nll_per_epoch"].append(epoch_nll / num_batches)
+        self.training_history = hist
+        return hist

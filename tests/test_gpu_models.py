@@ -227,3 +227,34 @@ def test_disc_qbm_training_accuracy_within_1pp_of_cpu_reference_loop(qbm, oracle
     acc_cpu = float(np.mean(np.array(pred_cpu) == yte))
     assert acc_cpu > 0.95 and acc_gpu > 0.95, (acc_gpu, acc_cpu)           # both learned the task
     assert abs(acc_gpu - acc_cpu) <= 0.01 + 1e-9, (acc_gpu, acc_cpu)
+
+
+def test_epoch_loops_and_checkpoints(qbm, cuda, tmp_path):
+    """L4 callers of the path: Disc_QBM.train_model (faster_dqbm.py:1079-1166) with per-epoch weight pickles in the
+    reference's format, load_savepoint (:169-190), and train.py::train_model for the Conv-Deep model."""
+    import pickle
+    rng = np.random.default_rng(3)
+    X = rng.random((40, 10)); y = (X[:, 0] > 0.5).astype(np.float64)
+    np.random.seed(1)
+    m = qbm.DiscQBM(dim_input=10, num_classes=2, n_hidden_nodes=4, epochs=3, sample_count=30, anneal_steps=100, seed=9,
+                    stats_mode="faster", speicherort=str(tmp_path) + "/", param_string="run")
+    hist = m.train_model(X, y, X[:20], y[:20], batch_size=16, learning_rate=0.3)
+    assert len(hist["acc_per_epoch"]) == 3 and len(hist["errors_per_batch"]) == 9      # 16 + 16 + 8 per epoch
+    assert all(0.0 <= a <= 1.0 for a in hist["acc_per_epoch"]) and np.isfinite(hist["nll_per_epoch"]).all()
+    saved = pickle.load(open(tmp_path / "run" / "e3_run.pkl", "rb"))
+    assert len(saved) == 6 and saved[0].shape == (11, 4) and saved[0].dtype == np.float64
+    for a, b in zip(saved, m.weight_objects):
+        assert np.array_equal(a, b)
+    np.random.seed(1)
+    m2 = qbm.DiscQBM(dim_input=10, num_classes=2, n_hidden_nodes=4, sample_count=30, anneal_steps=100, seed=9, stats_mode="faster")
+    m2.load_savepoint(str(tmp_path / "run" / "e3_run.pkl"))
+    assert np.array_equal(m2.predict_batch(X), m.predict_batch(X))
+    # the reference's own weight pickles have this layout too (785 x h for the 784-pixel models)
+    from qbm_b200.conv_deep_qbm import train_model
+    c = qbm.ConvDeepQBM(100, 1, image_shape=(10, 10), kernel_size=3, pooling_size=2, sequential_layer_sizes=[6],
+                        hidden_bias_type="shared", anneal=60, seed=4)
+    imgs = rng.random((7, 10, 10)).astype(np.float32)
+    losses = train_model(c, imgs, np.array([0, 1, 1, 0, 1, 0, 0]), 3, 2, 0.05, 20, 1.0)
+    assert len(losses) == 6 and np.isfinite(losses).all()
+    c.save_weights("cd", str(tmp_path))
+    assert len(pickle.load(open(tmp_path / "cd.pkl", "rb"))) == 8

@@ -199,6 +199,20 @@ def test_multi_kernel_batch_init_states_and_shared_stream(qbm, oracle, cuda):
         assert np.array_equal(got[b], ref), f"problem {b} (shared stream)"
 
 
+@pytest.mark.parametrize("flags", [0, 16, 32])
+def test_sweeps_per_beta_and_single_read(qbm, oracle, cuda, flags):
+    """num_sweeps > 1000 -> several sweeps per beta (neal: max(1, num_sweeps // 1000)); one read; all three kernels."""
+    n = 140
+    Q = random_qubo(n, seed=8)
+    h, J, betas, spb = _prep(qbm, Q, 2500)
+    assert spb == 2 and len(betas) == 1250
+    Jd, hd, bd = (torch.from_numpy(a).to(cuda) for a in (J, h, betas))
+    for reads in (1, 3):
+        got = qbm.sa_sample(Jd, hd, bd, spb, reads, 5, chain_offset=11, flags=flags).states.cpu().numpy()[0]
+        ref, _ = oracle.replay_sample(J, h, betas, spb, 5, 11, reads)
+        assert np.array_equal(got, ref)
+
+
 @pytest.mark.parametrize("n,R,B", [(1, 3, 1), (24, 100, 3), (34, 77, 2), (193, 130, 1), (522, 65, 1), (2048, 70, 1)])
 def test_energies_vs_oracle(qbm, oracle, cuda, n, R, B):
     rng = np.random.default_rng(n)
