@@ -298,7 +298,11 @@ def run_gpu(args):
         except (OSError, ValueError):
             pass
         roofline = {
-            "kernel": "sa_kernel<16,4,16,1>", "bound": "l1-shared-pipe", "achieved": achieved, "peak": l1_peak,
+            "kernel": "sa_kernel<16,4,16,1>", "bound": "l1-shared-pipe",
+            "bound_note": "neither of the contract's two rooflines applies: the sampler streams coupling rows through the "
+                          "L1/shared data pipe (ncu: l1tex data-pipe 76 %, DRAM 0.001 %, no tensor work); the HBM figures "
+                          "are reported under 'hbm', the FP32 pipe under 'fp32'",
+            "achieved": achieved, "peak": l1_peak,
             "unit": "GB/s", "frac": achieved / l1_peak, "traffic": traffic,
             "peak_source": f"derived: 128 B/clk/SM x {sm_count} SMs x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                            "the kernel streams coupling rows from L1, not HBM (SURVEY.md 8d)",

@@ -76,9 +76,12 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *   states_out   [batch_q, num_reads, n] int8 0/1, read order (what dimod calls record.sample)
  *   counters     nullable uint64[2]: += accepted flips, += proposals
  *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned
- *   flags        bit 0: disable the per-window CTA rendezvous (debug / A-B measurements)
+ *   flags        bit 0: disable the per-window CTA rendezvous of the default kernel (debug / A-B measurements;
+ *                       problems of up to 256 variables never rendezvous)
  *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
  *                       stream, as the reference's fixed per-call seed does)
+ *                bit 5: use the multi-chain warp kernel (a warp anneals 2-4 chains of one problem and shares their
+ *                       coupling-row loads; identical trajectories, n > 128 and num_reads >= 2 only)
  *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed
  *                       by TMA through a shared-memory ring; identical trajectories);
  *                       bits 8..15: its dense/sparse update switch in percent of flipped (chain, variable)
