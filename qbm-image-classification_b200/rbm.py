@@ -263,3 +263,37 @@ class B200ClassificationRBM:
 
     def predict(self, input_data):
         return self.sample_class_given_x(input_data).argmax(dim=1)
+
+    # ---- epoch loop (src/ClassificationRBM.py:159-205) ---------------------------------------------------------------
+    def train_rbm(self, train_loader, epochs, cuda=True, validation_loader=None, test_loader=None, method="discriminative",
+                  generative_factor=None, discriminative_factor=1):
+        """Same loop and return value ``(loss_list, best_validation_model, nll_list)`` as the reference; ``method`` may
+        also be ``"cd1"`` (the reference raises NotImplementedError for everything but ``"discriminative"``).  Accuracy on
+        ``test_loader`` is appended to ``acc_per_epoch_list`` after every epoch when a loader is given."""
+        if method not in ("discriminative", "cd1"):
+            raise NotImplementedError(method)
+        loss_list, nll_list = [], []
+        for _ in range(epochs):
+            epoch_error, epoch_nll, nb = 0.0, 0.0, 0
+            for batch, labels in train_loader:
+                batch = torch.as_tensor(batch).reshape(len(batch), self.num_visible)
+                labels = torch.as_tensor(labels).to(self.device)
+                if method == "discriminative":
+                    err, _, probs = self.discriminative_training(batch, labels, factor=discriminative_factor)
+                    nll = -torch.log(probs + 1e-8)[torch.arange(len(batch), device=self.device), labels.long()]
+                    epoch_error += float(err)
+                    epoch_nll += float(nll.mean())
+                else:
+                    self.cd1_training(batch, labels)
+                nb += 1
+            loss_list.append(epoch_error / max(1, nb))
+            nll_list.append(epoch_nll / max(1, nb))
+            if test_loader is not None:
+                correct = total = 0
+                for batch, labels in test_loader:
+                    batch = torch.as_tensor(batch).reshape(len(batch), self.num_visible)
+                    pred = self.predict(batch).cpu()
+                    correct += int((pred == torch.as_tensor(labels).long().cpu()).sum())
+                    total += len(batch)
+                self.acc_per_epoch_list.append(correct / max(1, total))
+        return loss_list, self, nll_list

@@ -158,3 +158,20 @@ def test_rbm_cd1_step_statistics(qbm, cuda):
     m2.class_weights = U0
     m2.cd1_training(xt, yt)
     assert torch.equal(m2.weights, m.weights) and torch.equal(m2.class_bias, m.class_bias)
+
+
+def test_train_rbm_epoch_loop(qbm, cuda):
+    """ClassificationRBM.train_rbm (src/ClassificationRBM.py:159-205): loader of (batch, labels) pairs, returns
+    (loss_list, model, nll_list); the loss falls and the test accuracy beats chance on separable synthetic data."""
+    rng = np.random.default_rng(0)
+    templates = rng.random((4, 64)) < 0.5
+    y = rng.integers(0, 4, 512)
+    x = (rng.random((512, 64)) < (0.15 + 0.7 * templates[y])).astype(np.float32)
+    loader = [(torch.from_numpy(x[i:i + 64]).reshape(64, 8, 8), torch.from_numpy(y[i:i + 64])) for i in range(0, 448, 64)]
+    test = [(torch.from_numpy(x[448:]), torch.from_numpy(y[448:]))]
+    m = qbm.B200ClassificationRBM(64, 32, 1, num_classes=4, learning_rate=0.5, seed=1)
+    losses, model, nlls = m.train_rbm(loader, 12, test_loader=test)
+    assert model is m and len(losses) == 12 and len(nlls) == 12
+    assert nlls[-1] < nlls[0] and m.acc_per_epoch_list[-1] > 0.8
+    with pytest.raises(NotImplementedError):
+        m.train_rbm(loader, 1, method="generative")
