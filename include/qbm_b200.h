@@ -76,8 +76,8 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *   states_out   [batch_q, num_reads, n] int8 0/1, read order (what dimod calls record.sample)
  *   counters     nullable uint64[2]: += accepted flips, += proposals
  *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned
- *   flags        bit 0: disable the per-window CTA rendezvous of the default kernel (debug / A-B measurements;
- *                       problems of up to 256 variables never rendezvous)
+ *   flags        bit 0: make the warps of a CTA rendezvous at every 128-variable window (A-B measurements; off by
+ *                       default because it measured slower)
  *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
  *                       stream, as the reference's fixed per-call seed does)
  *                bit 5: use the multi-chain warp kernel (a warp anneals 2-4 chains of one problem and shares their

@@ -9,10 +9,9 @@
 //   * the chain's n local fields live in registers, 4*NW per lane (variable v = w*128 + k*32 + lane
 //     is register F[w][k] of `lane`); spins are 4*NW bits per lane
 //   * the coupling matrix is stored column-permuted (p128_pos) so the four fields of a lane are one
-//     128-bit load per window; rows stream through L1 (read-only path), and the warps of a CTA
-//     rendezvous once per 128-variable window so that concurrently annealed chains touch the same
-//     rows while they are L1-resident (the sweep order is fixed, so every chain needs row v at
-//     step v)
+//     128-bit load per window; rows stream through L1 (read-only path): the sweep order is fixed, so
+//     the chains of an SM need row v at about the same time and mostly find it L1-resident (91 % hit
+//     rate at n = 2048)
 //   * proposals are evaluated 32 at a time (one sub-window of 32 consecutive variables, one per lane):
 //     because the uniform for (chain, sweep, v) is a pure function of its index (Philox4x32-10), the
 //     first accepted proposal of the sub-window is found with one ballot, every earlier proposal is
@@ -59,9 +58,10 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     const unsigned long long chain = p.chain_offset + (unsigned long long)((p.flags & 2u) ? (cl - q * p.num_reads) : cl);
     const uint32_t c_lo = (uint32_t)chain, c_hi = (uint32_t)(chain >> 32);
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-    // the per-window rendezvous keeps concurrently annealed chains on the same coupling rows while those are in L1;
-    // a problem of up to two windows (<= 256 KB of couplings) stays L1/L2-resident anyway and the barrier only costs
-    const bool rendezvous = (p.flags & 1u) == 0 && NW >= 3;
+    // optional per-window rendezvous of the CTA's warps (flag bit 0).  Off by default: chains that anneal the same problem
+    // stay on nearby coupling rows by themselves (a leading warp takes the L1 misses and is caught up by the others), and
+    // the barrier measured 0..17 % slower (n = 384..2048)
+    const bool rendezvous = (p.flags & 1u) != 0u && NW >= 3;
     const int nw_rt = (n + 127) >> 7;             // windows actually populated (<= NW)
 
     float F[NW][4];

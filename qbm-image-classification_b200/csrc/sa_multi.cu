@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_multi_kernel(const SaParams
     const float *__restrict__ hq = p.hp + (size_t)q * (size_t)ld;
     const float *__restrict__ betas = p.beta + q * p.beta_stride;
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-    const bool rendezvous = (p.flags & 1u) == 0;
+    const bool rendezvous = (p.flags & 1u) != 0u;
     const int nw_rt = (n + 127) >> 7;
 
     // chain t of this warp: read r0 + t of problem q (reads past num_reads shadow the last read and are not written)

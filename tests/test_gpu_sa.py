@@ -98,9 +98,13 @@ def test_sharding_invariance(qbm, cuda):
     a = qbm.sa_sample(Jd, hd, bd, spb, reads // 2, 9, chain_offset=0).states
     b = qbm.sa_sample(Jd, hd, bd, spb, reads // 2, 9, chain_offset=reads // 2).states
     assert torch.equal(full[0], torch.cat([a[0], b[0]], dim=0))
-    # the CTA rendezvous is a performance hint only: results are identical without it
-    nosync = qbm.sa_sample(Jd, hd, bd, spb, reads, 9, flags=1).states
-    assert torch.equal(full, nosync)
+    # the optional CTA rendezvous is a scheduling hint only: results are identical with it
+    sync = qbm.sa_sample(Jd, hd, bd, spb, reads, 9, flags=1).states
+    assert torch.equal(full, sync)
+    Q5 = random_qubo(600, seed=6)
+    h5, J5, b5, spb5 = _prep(qbm, Q5, 100)
+    a5 = [torch.from_numpy(a).to(cuda) for a in (J5, h5, b5)]
+    assert torch.equal(qbm.sa_sample(*a5, spb5, 19, 9).states, qbm.sa_sample(*a5, spb5, 19, 9, flags=1).states)
 
 
 # ---- the chain-tile kernel (sa_tile.cu): same trajectories, rows shared by 16 chains -------------------
