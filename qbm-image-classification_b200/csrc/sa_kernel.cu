@@ -10,7 +10,7 @@
 //     is register F[w][k] of `lane`); spins are 4*NW bits per lane
 //   * the coupling matrix is stored column-permuted (p128_pos) so the four fields of a lane are one
 //     128-bit load per window; rows stream through L1 (read-only path): the sweep order is fixed, so
-//     the chains of an SM need row v at about the same time and mostly find it L1-resident (91 % hit
+//     the chains of an SM need row v at about the same time and mostly find it L1-resident (87 % hit
 //     rate at n = 2048)
 //   * proposals are evaluated 32 at a time (one sub-window of 32 consecutive variables, one per lane):
 //     because the uniform for (chain, sweep, v) is a pure function of its index (Philox4x32-10), the
