@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import _lib, ising
+from . import _lib, dist as _d, ising
 
 
 def _stream_ptr(device) -> int:
@@ -158,12 +158,28 @@ def qubo_to_ising_device(Q: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 # host-level call: numpy QUBOs in, numpy samples out (what the reference's call sites exchange)
 # ------------------------------------------------------------------------------------------------
+def _all_gather_reads(local: torch.Tensor, num_reads: int, group) -> torch.Tensor:
+    """Concatenate the read shards of all ranks along dim 1 (reads): [B, hi - lo, ...] -> [B, num_reads, ...]."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    width = max(b - a for a, b in (_d.shard_range(num_reads, world, r) for r in range(world)))
+    pad = torch.zeros((local.shape[0], width) + tuple(local.shape[2:]), dtype=local.dtype, device=local.device)
+    pad[:, :local.shape[1]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([parts[r][:, :b - a] for r, (a, b) in ((r, _d.shard_range(num_reads, world, r)) for r in range(world))], dim=1)
+
+
 def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, seed=None, beta_range=None,
                       beta_schedule_type: str = "geometric", initial_states_generator: str = "numpy",
-                      device=None, return_energy: bool = True, chain_offset: int = 0):
+                      device=None, return_energy: bool = True, chain_offset: int = 0, process_group=None):
     """Sample a batch of dense QUBOs ``[B, n, n]`` (float64, host).  Host logic (spin conversion, beta
     range, schedule, initial states) follows neal/dimod in float64 (:mod:`ising`); the annealing, the
     energies and nothing else run on the GPU.
+
+    With ``process_group`` (one process per GPU) the reads are sharded over the ranks -- rank r anneals the
+    contiguous block ``dist.shard_range(num_reads, world, r)`` keyed by the global read index, so the result does not
+    depend on the number of GPUs -- and all-gathered, so that every rank returns all ``num_reads`` samples in read order.
 
     Returns ``(samples int8 [B, R, n] numpy, energies float64 [B, R] numpy or None, info dict)``.
     """
@@ -185,20 +201,34 @@ def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, see
     Jd = torch.from_numpy(J.astype(np.float32)).to(dev, non_blocking=True)
     hd = torch.from_numpy(h.astype(np.float32)).to(dev, non_blocking=True)
     bd = torch.from_numpy(betas.astype(np.float32)).to(dev, non_blocking=True)
+    lo, hi = 0, int(num_reads)
+    if process_group is not None:
+        import torch.distributed as dist
+        lo, hi = _d.shard_range(int(num_reads), dist.get_world_size(process_group), dist.get_rank(process_group))
+        if B > 1:
+            raise ValueError("read sharding over a process group supports one problem per call")
     init = None
     if initial_states_generator == "numpy":
         # the reference passes the same seed on every call, so every problem of the batch starts
         # from the same RandomState(seed) draw
-        st0 = ising.initial_states_numpy(seed, num_reads, n)
-        init = torch.from_numpy(np.broadcast_to(st0, (B, num_reads, n)).copy()).to(dev)
+        st0 = ising.initial_states_numpy(seed, num_reads, n)[lo:hi]
+        init = torch.from_numpy(np.broadcast_to(st0, (B, hi - lo, n)).copy()).to(dev)
     elif initial_states_generator != "philox":
         raise ValueError("initial_states_generator must be 'numpy' or 'philox'")
-    res = sa_sample(Jd, hd, bd, spb, num_reads, seed, chain_offset=chain_offset, init_states=init)
+    states = torch.empty((B, 0, n), dtype=torch.int8, device=dev)
+    if hi > lo:
+        states = sa_sample(Jd, hd, bd, spb, hi - lo, seed, chain_offset=chain_offset + lo, init_states=init).states
     energies = None
     if return_energy:
         Qd = torch.from_numpy(Q).to(dev)
-        energies = qubo_energies(Qd, res.states).cpu().numpy()
-    samples = res.states.cpu().numpy()
+        energies = qubo_energies(Qd, states) if hi > lo else torch.empty((B, 0), dtype=torch.float64, device=dev)
+    if process_group is not None:
+        states = _all_gather_reads(states, int(num_reads), process_group)
+        if energies is not None:
+            energies = _all_gather_reads(energies, int(num_reads), process_group)
+    if energies is not None:
+        energies = energies.cpu().numpy()
+    samples = states.cpu().numpy()
     info = {"beta_range": br.tolist() if not single else br[0].tolist(), "beta_schedule_type": beta_schedule_type,
             "num_betas": int(betas.shape[1]), "sweeps_per_beta": spb, "offset": offset}
     return samples, energies, info
@@ -208,11 +238,12 @@ class B200SASampler:
     """Drop-in for ``LocalSASampler`` (src/qubo/sampler.py:19-33)."""
 
     def __init__(self, num_sweeps: int = 1000, seed: int | None = None, initial_states_generator: str = "numpy",
-                 device=None):
+                 device=None, process_group=None):
         self.num_sweeps = int(num_sweeps)
         self.seed = seed
         self.initial_states_generator = initial_states_generator
         self.device = device
+        self.process_group = process_group      # reads sharded over the ranks, all samples returned on every rank
 
     def sample_Q(self, Q: np.ndarray, num_reads: int) -> np.ndarray:
         Q = np.asarray(Q, dtype=np.float64)
@@ -222,7 +253,7 @@ class B200SASampler:
             return _solve_linear_only(Q, int(num_reads), self.seed)
         samples, _, _ = sample_qubo_batch(Q, int(num_reads), self.num_sweeps, self.seed,
                                           initial_states_generator=self.initial_states_generator,
-                                          device=self.device, return_energy=False)
+                                          device=self.device, return_energy=False, process_group=self.process_group)
         return samples[0].astype(np.float32)
 
 

@@ -79,6 +79,10 @@ def _worker(rank, world, port, out_dir):
         part, _, _ = qbm_b200.sample_qubo_batch(Q, hi - lo, 200, seed=9, initial_states_generator="philox", device=dev,
                                                 return_energy=False, chain_offset=lo)
         res["sa"] = float(np.abs(full[0, lo:hi].astype(int) - part[0].astype(int)).max())
+        # the sharded drop-in: every rank gets all reads, identical to the single-GPU call (uneven shards: 33 reads)
+        one = qbm_b200.B200SASampler(num_sweeps=200, seed=9, device=dev).sample_Q(Q, 33)
+        both = qbm_b200.B200SASampler(num_sweeps=200, seed=9, device=dev, process_group=pg).sample_Q(Q, 33)
+        res["sa_gather"] = float(np.abs(one - both).max()) + (0.0 if both.shape == (33, 150) else 1.0)
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), res, allow_pickle=True)
     finally:
         dist.destroy_process_group()
@@ -96,3 +100,4 @@ def test_two_gpu_data_parallel_equals_single_gpu(tmp_path):
         assert res["convdeep"] < 1e-9, res
         assert res["rbm"] < 2e-5, res            # float32 parameters, TF32 products
         assert res["sa"] == 0.0, res             # bit-identical reads
+        assert res["sa_gather"] == 0.0, res      # sharded + all-gathered sample_Q == single-GPU sample_Q
