@@ -56,17 +56,20 @@ __global__ void __launch_bounds__(256) disc_build_qubo_kernel(const double *__re
     }
     __syncthreads();
     double *q = Q + b * (size_t)n * (size_t)n;
-    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
-        const int r = e / n, c = e % n;
-        double v = (r == c) ? diag[r] : 0.0;
-        if (clamped) {
-            if (Whh != nullptr) v += Whh[(size_t)r * h + c];
-        } else {
-            if (r < no && c >= no) v += Wvh[(size_t)r * h + (c - no)];          // output -> hidden couplings
-            else if (r < no && c < no) v += Woo[(size_t)r * no + c];
-            else if (r >= no && c >= no && Whh != nullptr) v += Whh[(size_t)(r - no) * h + (c - no)];
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int r = threadIdx.x >> 5; r < n; r += nwarps) {                         // one warp per row, lanes over columns
+        double *qr = q + (size_t)r * n;
+        for (int c = lane; c < n; c += 32) {
+            double v = (r == c) ? diag[r] : 0.0;
+            if (clamped) {
+                if (Whh != nullptr) v += Whh[(size_t)r * h + c];
+            } else {
+                if (r < no && c >= no) v += Wvh[(size_t)r * h + (c - no)];      // output -> hidden couplings
+                else if (r < no && c < no) v += Woo[(size_t)r * no + c];
+                else if (r >= no && c >= no && Whh != nullptr) v += Whh[(size_t)(r - no) * h + (c - no)];
+            }
+            qr[c] = v / beta_eff;
         }
-        q[e] = v / beta_eff;
     }
 }
 

@@ -71,6 +71,20 @@ def default_beta_range(h: np.ndarray, J: np.ndarray) -> np.ndarray:
     return out
 
 
+def beta_range_from_reductions(min_delta: np.ndarray, max_delta: np.ndarray) -> np.ndarray:
+    """The same rule from its two reductions (K0's ``range`` output: smallest non-zero |bias|, largest total |bias|;
+    both 0 when every bias is zero)."""
+    mn = np.atleast_1d(np.asarray(min_delta, dtype=np.float64))
+    mx = np.atleast_1d(np.asarray(max_delta, dtype=np.float64))
+    out = np.empty((mn.shape[0], 2), dtype=np.float64)
+    empty = mx == 0.0
+    with np.errstate(divide="ignore"):
+        out[:, 0] = np.log(2) / mx
+        out[:, 1] = np.log(100) / mn
+    out[empty] = (0.1, 1.0)
+    return out
+
+
 def beta_schedule(beta_range: np.ndarray, num_sweeps: int, beta_schedule_type: str = "geometric"):
     """Returns ``(betas [B, num_betas] f64, sweeps_per_beta)`` exactly as neal's ``sample()`` builds them."""
     beta_range = np.atleast_2d(np.asarray(beta_range, dtype=np.float64))

@@ -192,14 +192,18 @@ def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, see
     seed = ising.check_seed(seed)
     if seed is None:
         seed = int(np.random.randint(2 ** 31))
-    h, J, offset = ising.qubo_to_ising(Q)
+    # BINARY -> SPIN and the two reductions of neal's beta rule run on the device (K0 reproduces the float64 host
+    # formulas of ising.py bit for bit, numpy's summation order included); the schedule itself is built on the host from
+    # those two numbers exactly as neal does (np.geomspace)
+    Qd = torch.from_numpy(Q).to(dev)
+    Jd, hd, off_d, rng_d = qubo_to_ising_device(Qd)
+    offset = off_d.cpu().numpy()
     if beta_range is None:
-        br = ising.default_beta_range(h, J)
+        r = rng_d.cpu().numpy()
+        br = ising.beta_range_from_reductions(r[:, 0], r[:, 1])
     else:
         br = np.broadcast_to(np.asarray(beta_range, dtype=np.float64), (B, 2))
     betas, spb = ising.beta_schedule(br, num_sweeps, beta_schedule_type)
-    Jd = torch.from_numpy(J.astype(np.float32)).to(dev, non_blocking=True)
-    hd = torch.from_numpy(h.astype(np.float32)).to(dev, non_blocking=True)
     bd = torch.from_numpy(betas.astype(np.float32)).to(dev, non_blocking=True)
     lo, hi = 0, int(num_reads)
     if process_group is not None:
@@ -220,7 +224,6 @@ def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, see
         states = sa_sample(Jd, hd, bd, spb, hi - lo, seed, chain_offset=chain_offset + lo, init_states=init).states
     energies = None
     if return_energy:
-        Qd = torch.from_numpy(Q).to(dev)
         energies = qubo_energies(Qd, states) if hi > lo else torch.empty((B, 0), dtype=torch.float64, device=dev)
     if process_group is not None:
         states = _all_gather_reads(states, int(num_reads), process_group)
