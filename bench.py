@@ -232,7 +232,7 @@ def run_gpu(args):
                                                 device=dev, chain_offset=(i * world + rank) * R)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
-    h2d = J.astype(np.float32).nbytes + h.astype(np.float32).nbytes + betas.astype(np.float32).nbytes + Q.nbytes
+    h2d = Q.nbytes + betas.astype(np.float32).nbytes       # the float64 QUBO and the fp32 schedule; J and h are built on the device
     d2h = smp.nbytes + en.nbytes
 
     # ---- training legs: QBM train images/s (configs 1, 3, 5) and the ClassificationRBM steps (config 2)
