@@ -48,7 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(s), hdr_t):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("QBM_NVCC_EXTRA", "").split(), "-c", s, "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)

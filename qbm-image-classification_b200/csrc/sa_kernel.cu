@@ -86,7 +86,10 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     if ((flags & 32u) && sa_multi_supported(nw, num_reads)) return sa_multi_launch(p, nw, st);
     // code shape per instantiation <NW, KS, WPC, MINB, UW, P2, PIN, SH> as measured (profiles/r1d_sa_kernel_variants_probe.log):
     // unrolled windows + shuffled coefficient up to 6 windows (+13..32 %), packed FMAs for 3..5 windows, no gain from any
-    // of them at 8 windows and more
+    // of them at 8 windows and more.  Also measured and not adopted: more registers per thread at the price of fewer resident
+    // warps (only 6 windows gain, +4..9 % with 2 instead of 3 CTAs per SM), and rows padded to 32 instead of 128 variables
+    // (a float / float2 tail load per row): the time of a flip follows the number of load instructions, which the register
+    // budget serialises, not the bytes, so a tail window costs what a full one does
     if (n <= 32) return launch_sa<1, 1, 8, 4, false, false, true, true>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4, false, false, true, true>(p, st);
     switch (nw) {
@@ -95,7 +98,7 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
         case 3: return launch_sa<3, 4, 8, 3, true, true, true, true>(p, st);
         case 4: return launch_sa<4, 4, 8, 3, true, true, false, true>(p, st);
         case 5: return launch_sa<5, 4, 8, 3, true, true, true, true>(p, st);
-        case 6: return launch_sa<6, 4, 8, 3, true, false, true, true>(p, st);
+        case 6: return launch_sa<6, 4, 8, 2, true, false, true, true>(p, st);
         case 8: return launch_sa<8, 4, 8, 2>(p, st);
         case 10: return launch_sa<10, 4, 16, 1>(p, st);
         case 12: return launch_sa<12, 4, 16, 1>(p, st);
