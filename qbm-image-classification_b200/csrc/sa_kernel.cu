@@ -6,7 +6,9 @@ using sa_warp::launch_sa;
 namespace {
 
 // column-permute + pad one batch of spin models into the workspace
-__global__ void sa_permute_kernel(const float *__restrict__ J, const float *__restrict__ h, int n, int ldj, int ld,
+// (rot > 0: row r is stored rotated by its own window, segment j holds window (r / 128 + j) % rot -- the layout of the
+// rotating-window kernels)
+__global__ void sa_permute_kernel(const float *__restrict__ J, const float *__restrict__ h, int n, int ldj, int ld, int rot,
                                   float *__restrict__ Jp, float *__restrict__ hp)
 {
     // grid: (n + 1, batch_q); row index n = the h vector
@@ -16,15 +18,18 @@ __global__ void sa_permute_kernel(const float *__restrict__ J, const float *__re
     float *dst = (row < n) ? Jp + (q * (size_t)n + row) * (size_t)ld : hp + q * (size_t)ld;
     for (int pos = threadIdx.x; pos < ld; pos += blockDim.x) {
         // inverse of p128_pos: storage position -> variable
-        const int v = (pos & ~127) | (((pos & 3) << 5) | ((pos >> 2) & 31));
+        const int seg = pos >> 7;
+        const int win = (rot > 0 && row < n) ? ((row >> 7) + seg) % rot : seg;
+        const int v = (win << 7) | (((pos & 3) << 5) | ((pos >> 2) & 31));
         dst[pos] = (v < n) ? src[v] : 0.0f;
     }
 }
 
 }  // namespace
 
-// number of 128-variable windows of the kernel instantiation that serves n (rows are padded to it)
-static inline int sa_variant_nw(int n)
+// number of 128-variable windows of the instantiation that serves n (rows are padded to it): the chains-per-warp kernel
+// (and the workspace size, which covers every kernel) ...
+static inline int sa_multi_nw(int n)
 {
     const int nw = (n + 127) / 128;
     if (nw <= 6) return nw;
@@ -33,12 +38,17 @@ static inline int sa_variant_nw(int n)
     if (nw <= 12) return 12;
     return 16;
 }
-static inline int sa_ld(int n) { return sa_variant_nw(n) * 128; }
+// ... and the warp-per-chain kernel
+static inline int sa_variant_nw(int n)
+{
+    const int nw = (n + 127) / 128;
+    return (nw == 13 || nw == 14) ? 14 : sa_multi_nw(n);
+}
 
 extern "C" QBM_API size_t qbm_sa_workspace_bytes(int n, long long batch_q)
 {
     if (n <= 0 || batch_q <= 0) return 0;
-    const size_t ld = (size_t)sa_ld(n);
+    const size_t ld = (size_t)sa_multi_nw(n) * 128;
     return (size_t)batch_q * ((size_t)n + 1) * ld * sizeof(float);
 }
 
@@ -67,11 +77,15 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     // kernel choice: the warp-per-chain kernel is the default (faster at every size measured in round 1:
     // 23.3 vs 15.4 G spin-updates/s at n = 2048); flag bit 4 selects the chain-tile kernel (sa_tile.cu)
     const bool tile = (flags & 16u) != 0u && sa_tile_supported(n);
-    const int ld = tile ? sa_tile_ld(n) : sa_ld(n);
+    const bool multi = !tile && (flags & 32u) != 0u && sa_multi_supported(sa_multi_nw(n), num_reads);
+    const int nw = multi ? sa_multi_nw(n) : sa_variant_nw(n);
+    const int ld = tile ? sa_tile_ld(n) : nw * 128;
     float *Jp = reinterpret_cast<float *>(workspace);
     float *hp = Jp + (size_t)batch_q * (size_t)n * (size_t)ld;
 
-    sa_permute_kernel<<<dim3((unsigned)n + 1, (unsigned)batch_q), 128, 0, st>>>(J, h, n, ldj, ld, Jp, hp);
+    // 8..14 windows run the rotating-window shape, whose rows are stored rotated (sa_warp.cuh)
+    const bool rt = !tile && !multi && nw >= 8 && nw <= 14;
+    sa_permute_kernel<<<dim3((unsigned)n + 1, (unsigned)batch_q), 128, 0, st>>>(J, h, n, ldj, ld, rt ? nw : 0, Jp, hp);
     QBM_LAUNCH_OK("sa_permute_kernel");
 
     SaParams p;
@@ -82,14 +96,14 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     p.Jnat = J; p.ldj = ldj; p.batch_q = batch_q;
     if (tile) return sa_tile_launch(p, st);
 
-    const int nw = sa_variant_nw(n);
-    if ((flags & 32u) && sa_multi_supported(nw, num_reads)) return sa_multi_launch(p, nw, st);
-    // code shape per instantiation <NW, KS, WPC, MINB, UW, P2, PIN, SH> as measured (profiles/r1d_sa_kernel_variants_probe.log):
-    // unrolled windows + shuffled coefficient up to 6 windows (+13..32 %), packed FMAs for 3..5 windows, no gain from any
-    // of them at 8 windows and more.  Also measured and not adopted: more registers per thread at the price of fewer resident
-    // warps (only 6 windows gain, +4..9 % with 2 instead of 3 CTAs per SM), and rows padded to 32 instead of 128 variables
-    // (a float / float2 tail load per row): the time of a flip follows the number of load instructions, which the register
-    // budget serialises, not the bytes, so a tail window costs what a full one does
+    if (multi) return sa_multi_launch(p, nw, st);
+    // code shape per instantiation <NW, KS, WPC, MINB, UW, P2, PIN, SH, RT>, each chosen by measurement
+    // (profiles/r1d_sa_kernel_*_probe.log): unrolled windows + shuffled coefficient up to 6 windows (+13..32 %), packed FMAs
+    // at 3..5 windows; at 8..14 windows the rotating-window shape removes the working copy instead (+8..14 %); at 16 windows
+    // (n = 2048, L1-bandwidth-bound with 128 registers) every one of them measured 0..-2 %.  Also measured and not adopted:
+    // more registers per thread for fewer resident warps (only 6 windows gain: 2 instead of 3 CTAs per SM), rows padded to 32
+    // instead of 128 variables (a float / float2 tail load per row; the time of a flip followed the number of windows, not
+    // the bytes), all loads of a row issued before its first FMA
     if (n <= 32) return launch_sa<1, 1, 8, 4, false, false, true, true>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4, false, false, true, true>(p, st);
     switch (nw) {
@@ -99,9 +113,10 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
         case 4: return launch_sa<4, 4, 8, 3, true, true, false, true>(p, st);
         case 5: return launch_sa<5, 4, 8, 3, true, true, true, true>(p, st);
         case 6: return launch_sa<6, 4, 8, 2, true, false, true, true>(p, st);
-        case 8: return launch_sa<8, 4, 8, 2>(p, st);
-        case 10: return launch_sa<10, 4, 16, 1>(p, st);
-        case 12: return launch_sa<12, 4, 16, 1>(p, st);
+        case 8: return launch_sa<8, 4, 8, 2, false, false, true, false, true>(p, st);
+        case 10: return launch_sa<10, 4, 16, 1, false, false, true, false, true>(p, st);
+        case 12: return launch_sa<12, 4, 16, 1, false, false, true, false, true>(p, st);
+        case 14: return launch_sa<14, 4, 16, 1, false, false, true, false, true>(p, st);
         default: return launch_sa<16, 4, 16, 1>(p, st);
     }
 }

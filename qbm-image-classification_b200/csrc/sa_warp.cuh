@@ -70,10 +70,22 @@ __device__ __forceinline__ void row_update(Win (&F)[NW], const float *__restrict
     for (int w2 = 0; w2 < NW; ++w2) win_update<P2>(F[w2], __ldg(reinterpret_cast<const float4 *>(row_lane + w2 * 128)), c);
 }
 
-template <int NW, int KS, int WPC, int MINB, bool UW, bool P2, bool PIN, bool SH>
+// RT: the windows rotate through the register sets, set 0 is always the window being swept (and row r is stored with its
+// own window first, see sa_permute_kernel), so the swept window is addressed statically without unrolling the window loop
+template <int NW>
+__device__ __forceinline__ void rotate_windows(Win (&F)[NW])
+{
+    const Win first = F[0];
+#pragma unroll
+    for (int j = 0; j + 1 < NW; ++j) F[j] = F[j + 1];
+    F[NW - 1] = first;
+}
+
+template <int NW, int KS, int WPC, int MINB, bool UW, bool P2, bool PIN, bool SH, bool RT>
 __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
 {
-    constexpr bool DIRECT = (NW == 1) || UW;      // the swept window's fields are addressed statically
+    constexpr bool DIRECT = (NW == 1) || UW || RT;      // the swept window's fields are addressed statically
+    static_assert(!(UW && RT), "unrolled or rotating windows, not both");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     long long cl = (long long)blockIdx.x * WPC + warp;
@@ -107,7 +119,12 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
         F[w].p[0] = make_float2(hv.x, hv.y);
         F[w].p[1] = make_float2(hv.z, hv.w);
     }
-    for (int w = 0; w < nw_rt; ++w) {
+#pragma unroll 1
+    for (int w = 0; w < (RT ? NW : nw_rt); ++w) {
+        if (RT && w >= nw_rt) {                   // empty window: only keep the rotation in step
+            rotate_windows<NW>(F);
+            continue;
+        }
         uint32_t wd[4];
         if (p.init != nullptr) {
 #pragma unroll
@@ -130,6 +147,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
                 row_update<NW, false>(F, J + (uint32_t)(jbase + jj) * (uint32_t)ld, sj);
             }
         }
+        if (RT) rotate_windows<NW>(F);
     }
 
     // ---- annealing ----
@@ -195,6 +213,12 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
 #pragma unroll
                 for (int w = 0; w < NW; ++w)
                     if (w < nw_rt) sweep_window(w, F[w]);
+            } else if (RT) {
+#pragma unroll 1
+                for (int w = 0; w < NW; ++w) {
+                    if (w < nw_rt) sweep_window(w, F[0]);
+                    rotate_windows<NW>(F);
+                }
             } else {
                 for (int w = 0; w < nw_rt; ++w) {
                     Win Fc;
@@ -226,10 +250,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     }
 }
 
-template <int NW, int KS, int WPC, int MINB, bool UW = false, bool P2 = false, bool PIN = (NW <= 2 || NW >= 6), bool SH = false>
+template <int NW, int KS, int WPC, int MINB, bool UW = false, bool P2 = false, bool PIN = (NW <= 2 || NW >= 6), bool SH = false,
+          bool RT = false>
 int launch_sa(const SaParams &p, cudaStream_t st)
 {
-    auto kern = sa_kernel<NW, KS, WPC, MINB, UW, P2, PIN, SH>;
+    auto kern = sa_kernel<NW, KS, WPC, MINB, UW, P2, PIN, SH, RT>;
     // all on-chip memory as L1: coupling rows are shared between the chains of an SM through L1
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
     const long long blocks = (p.total_chains + WPC - 1) / WPC;

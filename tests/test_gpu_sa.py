@@ -54,7 +54,8 @@ def test_device_neg_log_bit_exact(qbm, oracle, cuda):
     (1, 5, 50, 1.0), (7, 16, 200, 1.0), (24, 33, 1000, 1.0), (32, 9, 300, 1.0), (33, 9, 300, 1.0),
     (34, 40, 1000, 1.0), (64, 8, 300, 1.0), (65, 8, 300, 0.5), (100, 8, 400, 1.0), (128, 8, 300, 1.0),
     (129, 8, 300, 1.0), (193, 12, 1000, 0.89), (256, 6, 200, 1.0), (300, 6, 200, 1.0), (522, 6, 1000, 1.0),
-    (700, 4, 100, 1.0), (1000, 4, 100, 1.0), (1200, 3, 100, 1.0), (1500, 3, 100, 1.0), (2048, 3, 1000, 1.0),
+    (700, 4, 100, 1.0), (1000, 4, 100, 1.0), (1200, 3, 100, 1.0), (1500, 3, 100, 1.0), (1700, 3, 100, 1.0),
+    (2048, 3, 1000, 1.0),
 ])
 def test_trajectory_bit_exact_vs_replay(qbm, oracle, cuda, n, reads, sweeps, density):
     """The kernel's final states equal the sequential CPU replay of the reference's Metropolis rule fed
@@ -215,6 +216,23 @@ def test_sweeps_per_beta_and_single_read(qbm, oracle, cuda, flags):
         got = qbm.sa_sample(Jd, hd, bd, spb, reads, 5, chain_offset=11, flags=flags).states.cpu().numpy()[0]
         ref, _ = oracle.replay_sample(J, h, betas, spb, 5, 11, reads)
         assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("n", [900, 1290, 1650, 1792])
+def test_kernels_agree_where_their_row_layouts_differ(qbm, cuda, n):
+    """8..14 windows: the default kernel stores rows rotated by their own window, the chain-tile and chains-per-warp kernels
+    do not (and pad to 16 windows above 12) -- same states from all three, with host initial states and a batch of 2."""
+    reads = 6
+    Qs = np.stack([random_qubo(n, seed=300 + n + b) for b in range(2)])
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), 60)
+    init = np.stack([qbm.ising.initial_states_numpy(7 + b, reads, n) for b in range(2)])
+    args = [torch.from_numpy(a.astype(np.float32)).to(cuda) for a in (J, h, betas)]
+    initd = torch.from_numpy(init).to(cuda)
+    base = qbm.sa_sample(*args, spb, reads, 21, init_states=initd).states
+    for flags in (16, 32):
+        assert torch.equal(base, qbm.sa_sample(*args, spb, reads, 21, init_states=initd, flags=flags).states), flags
+    assert not torch.equal(base[0], base[1])
 
 
 @pytest.mark.parametrize("n,R,B", [(1, 3, 1), (24, 100, 3), (34, 77, 2), (193, 130, 1), (522, 65, 1), (2048, 70, 1)])
