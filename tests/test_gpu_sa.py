@@ -230,7 +230,7 @@ def test_kernels_agree_where_their_row_layouts_differ(qbm, cuda, n):
     args = [torch.from_numpy(a.astype(np.float32)).to(cuda) for a in (J, h, betas)]
     initd = torch.from_numpy(init).to(cuda)
     base = qbm.sa_sample(*args, spb, reads, 21, init_states=initd).states
-    for flags in (16, 32):
+    for flags in (16, 32, 1):           # chain-tile, chains-per-warp, default kernel with the CTA rendezvous
         assert torch.equal(base, qbm.sa_sample(*args, spb, reads, 21, init_states=initd, flags=flags).states), flags
     assert not torch.equal(base[0], base[1])
 
