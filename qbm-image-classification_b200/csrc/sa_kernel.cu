@@ -103,7 +103,8 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     // (n = 2048, L1-bandwidth-bound with 128 registers) every one of them measured 0..-2 %.  Also measured and not adopted:
     // more registers per thread for fewer resident warps (only 6 windows gain: 2 instead of 3 CTAs per SM), rows padded to 32
     // instead of 128 variables (a float / float2 tail load per row; the time of a flip followed the number of windows, not
-    // the bytes), all loads of a row issued before its first FMA
+    // the bytes), all loads of a row issued before its first FMA, a grid numbering that gives the CTAs of an SM consecutive
+    // chains of one problem (r1d_sa_kernel_sm_affine_grid_probe.log: -9..+8 %)
     if (n <= 32) return launch_sa<1, 1, 8, 4, false, false, true, true>(p, st);
     if (n <= 64) return launch_sa<1, 2, 8, 4, false, false, true, true>(p, st);
     switch (nw) {

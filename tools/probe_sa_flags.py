@@ -17,11 +17,12 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--sweeps", type=int, default=1000)
     ap.add_argument("--reads", type=int, default=0, help="reads per problem for n > 768 (default 2368)")
+    ap.add_argument("--small", default="64x200", help="problems x reads for n <= 768")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     flags = [int(x, 0) for x in a.flags.split(",")]
     for n in [int(x) for x in a.sizes.split(",")]:
-        batch, reads = (64, 200) if n <= 768 else (1, a.reads or 2368)
+        batch, reads = tuple(int(x) for x in a.small.split("x")) if n <= 768 else (1, a.reads or 2368)
         rng = np.random.default_rng(19)
         Q = np.stack([np.triu(rng.uniform(-1, 1, (n, n))) for _ in range(batch)])
         h, J, _ = qbm_b200.ising.qubo_to_ising(Q)
