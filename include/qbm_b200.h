@@ -75,19 +75,25 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *   init_states  nullable [batch_q, num_reads, n] int8 0/1; NULL = Philox initial states
  *   states_out   [batch_q, num_reads, n] int8 0/1, read order (what dimod calls record.sample)
  *   counters     nullable uint64[2]: += accepted flips, += proposals
- *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned
+ *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned.  With at least
+ *                qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads) bytes the sampler may run the two-phase
+ *                schedule (n > 1792: the chain-tile kernel anneals the hot sweeps, then hands every chain -- fields,
+ *                spins, sweep counter -- to the warp-per-chain kernel; identical results, ~1.2x faster at n = 2048)
  *   flags        bit 0: make the warps of a CTA rendezvous at every 128-variable window (A-B measurements; off by
  *                       default because it measured slower)
  *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
  *                       stream, as the reference's fixed per-call seed does)
  *                bit 5: use the multi-chain warp kernel (a warp anneals 2-4 chains of one problem and shares their
  *                       coupling-row loads; identical trajectories, n > 128 and num_reads >= 2 only)
+ *                bit 6: never use the two-phase schedule; bits 16..23: its hand-over threshold in percent of
+ *                       accepted proposals per sweep (0 = default 75)
  *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed
  *                       by TMA through a shared-memory ring; identical trajectories);
  *                       bits 8..15: its dense/sparse update switch in percent of flipped (chain, variable)
  *                       pairs per 32-variable sub-window (0 = default 40)
  */
 size_t qbm_sa_workspace_bytes(int n, long long batch_q);
+size_t qbm_sa_workspace_bytes_two_phase(int n, long long batch_q, long long num_reads);
 int qbm_sa_sample(const float *J, const float *h, int n, int ldj, long long batch_q,
                   const float *beta, long long beta_stride, int num_betas, int sweeps_per_beta,
                   long long num_reads, uint64_t seed, uint64_t chain_offset,

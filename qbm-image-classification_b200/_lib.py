@@ -32,6 +32,7 @@ SIGNATURES = {
     "qbm_qubo_to_ising": (_c_i, [_c_p, _c_i, _c_ll, _c_p, _c_p, _c_p, _c_p, _c_p]),
     "qbm_beta_schedule": (_c_i, [_c_p, _c_ll, _c_i, _c_p, _c_p]),
     "qbm_sa_workspace_bytes": (_c_sz, [_c_i, _c_ll]),
+    "qbm_sa_workspace_bytes_two_phase": (_c_sz, [_c_i, _c_ll, _c_ll]),
     "qbm_sa_sample": (_c_i, [_c_p, _c_p, _c_i, _c_i, _c_ll, _c_p, _c_ll, _c_i, _c_i, _c_ll, _c_u64, _c_u64,
                              _c_p, _c_p, _c_p, _c_p, _c_sz, _c_u, _c_p]),
     "qbm_qubo_energy": (_c_i, [_c_p, _c_i, _c_ll, _c_p, _c_ll, _c_p, _c_p]),

@@ -23,6 +23,12 @@ struct SaParams {
     unsigned long long *counters;
     unsigned flags;
     long long batch_q;
+    // two-phase schedule (qbm_sa_sample with a large workspace): the chain-tile kernel anneals the hot sweeps and hands its
+    // chains over -- fields in the warp kernel's register layout, sweeps done per chain, spins through `out` -- to the
+    // warp-per-chain kernel, which resumes them (same trajectory)
+    float *fields;            // nullable [total_chains, ld]
+    uint32_t *sweeps_done;    // nullable [tiles]: completed sweeps per tile of 16 chains
+    float hot_fraction;       // tile kernel: stop after the first sweep whose accepted fraction is below this (0 = never)
 };
 
 // sa_tile.cu

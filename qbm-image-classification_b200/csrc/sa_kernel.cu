@@ -52,6 +52,17 @@ extern "C" QBM_API size_t qbm_sa_workspace_bytes(int n, long long batch_q)
     return (size_t)batch_q * ((size_t)n + 1) * ld * sizeof(float);
 }
 
+// two-phase schedule (chain-tile kernel for the hot sweeps, then one warp per chain): used where it measured faster
+static inline bool sa_two_phase_size(int n) { return n > 1792; }
+
+extern "C" QBM_API size_t qbm_sa_workspace_bytes_two_phase(int n, long long batch_q, long long num_reads)
+{
+    const size_t base = qbm_sa_workspace_bytes(n, batch_q);
+    if (base == 0 || num_reads <= 0 || !sa_two_phase_size(n)) return base;
+    const size_t chains = (size_t)batch_q * (size_t)num_reads;
+    return base + chains * (size_t)sa_multi_nw(n) * 128 * sizeof(float) + ((chains * sizeof(uint32_t) + 15) / 16) * 16;
+}
+
 extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int ldj, long long batch_q,
                              const float *beta, long long beta_stride, int num_betas, int sweeps_per_beta,
                              long long num_reads, uint64_t seed, uint64_t chain_offset,
@@ -94,7 +105,27 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     p.total_chains = batch_q * num_reads; p.seed = seed; p.chain_offset = chain_offset;
     p.init = init_states; p.out = states_out; p.counters = counters; p.flags = flags;
     p.Jnat = J; p.ldj = ldj; p.batch_q = batch_q;
+    p.fields = nullptr; p.sweeps_done = nullptr; p.hot_fraction = 0.0f;
     if (tile) return sa_tile_launch(p, st);
+
+    // two-phase schedule: in the hot sweeps nearly every chain flips nearly every variable, so the chain-tile kernel (one
+    // fetch of a coupling row for 16 chains) is faster there (58 vs 86 clocks per flip and SM at n = 2048) and the
+    // warp-per-chain kernel everywhere else; the tile kernel hands a chain over after the first sweep that accepts less than
+    // hot_fraction of its proposals.  Both kernels follow the same trajectory, so the cut does not change any result.
+    // Needs the larger workspace (qbm_sa_workspace_bytes_two_phase); flag bit 6 switches it off.
+    if (!multi && sa_two_phase_size(n) && (flags & 64u) == 0u && sa_tile_supported(n) && sa_tile_ld(n) == ld &&
+        workspace_bytes >= qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads)) {
+        const unsigned pct = (flags >> 16) & 0xffu;
+        SaParams hot = p;
+        hot.fields = hp + (size_t)batch_q * (size_t)ld;
+        hot.sweeps_done = reinterpret_cast<uint32_t *>(hot.fields + (size_t)p.total_chains * (size_t)ld);
+        hot.hot_fraction = pct ? (float)pct / 100.0f : 0.75f;
+        if (const int rc = sa_tile_launch(hot, st)) return rc;
+        // the resuming instantiation (RS) starts from fields / sweeps_done / init instead of computing the initial fields
+        p.fields = hot.fields; p.sweeps_done = hot.sweeps_done;
+        p.init = states_out;
+        return launch_sa<16, 4, 16, 1, false, false, true, false, false, true>(p, st);
+    }
 
     if (multi) return sa_multi_launch(p, nw, st);
     // code shape per instantiation <NW, KS, WPC, MINB, UW, P2, PIN, SH, RT>, each chosen by measurement

@@ -418,11 +418,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     // ---- annealing ----
     unsigned long long nacc = 0ull;
     uint32_t t_sweep = 0;
+    bool handed_over = false;
+    const unsigned long long hot_min =
+        p.hot_fraction > 0.0f ? (unsigned long long)((double)p.hot_fraction * (double)n * (double)nlive) : 0ull;
     uint32_t pi = 0;                                   // running sub-window counter: parity of the record buffers
-    for (int b = 0; b < p.num_betas; ++b) {
+    for (int b = 0; b < p.num_betas && !handed_over; ++b) {
         const float beta = __ldg(betas + b);
         const float thr = __fdiv_rn(44.36142f, beta);
-        for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++t_sweep) {
+        for (int sw = 0; sw < p.sweeps_per_beta && !handed_over; ++sw, ++t_sweep) {
+            const unsigned long long nacc_before = nacc;
             int bounds_window = -1;
             for (int s = 0; s < S; ++s, ++pi) {
                 const int g = s >> 2, k = s & 3;
@@ -562,9 +566,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
                     apply_record<NS>(F2, A, sm.rec_meta[par * 4 + 0], sm.rec_meta[par * 4 + 1], par, lane, ri, dense_min);
                 }
             }
+            // two-phase schedule: once a sweep accepts less than hot_fraction of its proposals the chains are cheaper to
+            // advance one warp each (rows no longer shared by most chains); every consumer thread sees the same counts
+            if (hot_min > 0ull && nacc - nacc_before < hot_min) handed_over = true;
         }
     }
     consumer_sync(ncons);
+    if (p.fields != nullptr) {
+        // fields in the warp kernel's layout: chain-major, float4 (sub-windows 0..3) per lane and 128-variable window
+#pragma unroll
+        for (int jw = 0; jw < NWIN; ++jw) {
+            const size_t off = (size_t)(jw * W + warp) * 128 + (size_t)lane * 4;
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                if (t < nlive)
+                    *reinterpret_cast<float4 *>(p.fields + (size_t)(cl0 + t) * (size_t)ld + off) =
+                        make_float4(F2[jw * 2][t].x, F2[jw * 2][t].y, F2[jw * 2 + 1][t].x, F2[jw * 2 + 1][t].y);
+        }
+        if (tid == 0) p.sweeps_done[blockIdx.x] = t_sweep;            // completed sweeps of this tile
+    }
 
     // ---- write-back: states in natural variable order, 0/1; stop the producer ----
     if (tid == 0) {

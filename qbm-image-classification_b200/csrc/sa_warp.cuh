@@ -81,15 +81,20 @@ __device__ __forceinline__ void rotate_windows(Win (&F)[NW])
     F[NW - 1] = first;
 }
 
-template <int NW, int KS, int WPC, int MINB, bool UW, bool P2, bool PIN, bool SH, bool RT>
+template <int NW, int KS, int WPC, int MINB, bool UW, bool P2, bool PIN, bool SH, bool RT, bool RS>
 __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
 {
     constexpr bool DIRECT = (NW == 1) || UW || RT;      // the swept window's fields are addressed statically
     static_assert(!(UW && RT), "unrolled or rotating windows, not both");
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    long long cl = (long long)blockIdx.x * WPC + warp;
-    const bool live = cl < p.total_chains;
+    // RS (resuming the chains of the chain-tile kernel): a CTA is one of its tiles of 16 chains of one problem, so that the
+    // first sweep (sweeps_done[tile]) is a CTA-uniform value and the sweep loops stay uniform for the compiler
+    static_assert(!RS || WPC == 16, "a resuming CTA is one tile of the chain-tile kernel");
+    const long long tiles_per_problem = (p.num_reads + WPC - 1) / WPC;
+    long long cl = RS ? (blockIdx.x / tiles_per_problem) * p.num_reads + (blockIdx.x % tiles_per_problem) * WPC + warp
+                      : (long long)blockIdx.x * WPC + warp;
+    const bool live = RS ? ((blockIdx.x % tiles_per_problem) * WPC + warp < p.num_reads) : (cl < p.total_chains);
     if (!live) cl = p.total_chains - 1;           // idle warps shadow the last chain (they keep the barriers matched)
     const long long q = cl / p.num_reads;
     const int n = p.n;
@@ -113,9 +118,13 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
     unsigned long long spins = 0ull;              // bit (w*4+k) = spin of variable w*128 + k*32 + lane (1 = up)
 
     // ---- initial spins and local fields: F_i = h_i ; for j = 0..n-1: F_i = fma(J[j][i], s_j, F_i) ----
+    // resuming chains handed over by the chain-tile kernel: fields as it left them (same register layout), spins from
+    // p.init (= the states it wrote), first sweep = sweeps_done[chain]
+    constexpr bool resume = RS;
+    const float *__restrict__ f0 = resume ? p.fields + (size_t)cl * (size_t)ld : hq;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-        const float4 hv = __ldg(reinterpret_cast<const float4 *>(hq + w * 128 + lane * 4));
+        const float4 hv = __ldg(reinterpret_cast<const float4 *>(f0 + w * 128 + lane * 4));
         F[w].p[0] = make_float2(hv.x, hv.y);
         F[w].p[1] = make_float2(hv.z, hv.w);
     }
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
         for (int k = 0; k < 4; ++k) {
             spins |= (unsigned long long)((wd[k] >> lane) & 1u) << (w * 4 + k);
             const int jbase = w * 128 + k * 32;
-            const int jend = min(32, n - jbase);
+            const int jend = resume ? 0 : min(32, n - jbase);
             for (int jj = 0; jj < jend; ++jj) {
                 const float sj = ((wd[k] >> jj) & 1u) ? 1.0f : -1.0f;
                 row_update<NW, false>(F, J + (uint32_t)(jbase + jj) * (uint32_t)ld, sj);
@@ -152,11 +161,11 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
 
     // ---- annealing ----
     uint32_t nacc = 0;
-    uint32_t t = 0;
-    for (int b = 0; b < p.num_betas; ++b) {
+    uint32_t t = resume ? p.sweeps_done[blockIdx.x] : 0u;
+    for (int b = resume ? (int)(t / (uint32_t)p.sweeps_per_beta) : 0; b < p.num_betas; ++b) {
         const float beta = __ldg(betas + b);
         const float thr = __fdiv_rn(44.36142f, beta);
-        for (int s = 0; s < p.sweeps_per_beta; ++s, ++t) {
+        for (int s = resume ? (int)(t - (uint32_t)b * (uint32_t)p.sweeps_per_beta) : 0; s < p.sweeps_per_beta; ++s, ++t) {
             // one window: 4 sub-windows of 32 proposals; Fc = the window's four fields (the fields themselves when the
             // window index is static, else a working copy: register indices must be compile-time)
             auto sweep_window = [&](const int w, Win &Fc) {
@@ -245,19 +254,19 @@ __global__ void __launch_bounds__(WPC * 32, MINB) sa_kernel(const SaParams p)
         }
         if (p.counters != nullptr && lane == 0) {
             atomicAdd(p.counters + 0, (unsigned long long)nacc);
-            atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)t);
+            atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)(t - (resume ? p.sweeps_done[blockIdx.x] : 0u)));
         }
     }
 }
 
 template <int NW, int KS, int WPC, int MINB, bool UW = false, bool P2 = false, bool PIN = (NW <= 2 || NW >= 6), bool SH = false,
-          bool RT = false>
+          bool RT = false, bool RS = false>
 int launch_sa(const SaParams &p, cudaStream_t st)
 {
-    auto kern = sa_kernel<NW, KS, WPC, MINB, UW, P2, PIN, SH, RT>;
+    auto kern = sa_kernel<NW, KS, WPC, MINB, UW, P2, PIN, SH, RT, RS>;
     // all on-chip memory as L1: coupling rows are shared between the chains of an SM through L1
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
-    const long long blocks = (p.total_chains + WPC - 1) / WPC;
+    const long long blocks = RS ? ((p.num_reads + WPC - 1) / WPC) * p.batch_q : (p.total_chains + WPC - 1) / WPC;
     if (blocks > 0x7fffffffLL) {
         qbm_set_error("qbm_sa_sample: too many chains for one launch (%lld)", p.total_chains);
         return QBM_EUNSUPPORTED;

@@ -67,7 +67,8 @@ def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_
     num_betas = betas.shape[1]
     beta_stride = 0 if betas.shape[0] == 1 else num_betas
     dev = J.device
-    need = L.qbm_sa_workspace_bytes(n, bq)
+    # the larger workspace lets the library run its two-phase schedule where that is faster (n > 1792)
+    need = L.qbm_sa_workspace_bytes_two_phase(n, bq, int(num_reads))
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 15) // 16 * 4, dtype=torch.float32, device=dev)
     if out is None:

@@ -218,6 +218,29 @@ def test_sweeps_per_beta_and_single_read(qbm, oracle, cuda, flags):
         assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n,reads,sweeps,pct", [(2048, 20, 60, 0), (1800, 35, 40, 0), (1930, 17, 50, 97), (2048, 16, 30, 1),
+                                                (2000, 5, 25, 100)])
+def test_two_phase_schedule_is_the_same_trajectory(qbm, oracle, cuda, n, reads, sweeps, pct):
+    """n > 1792: the chain-tile kernel anneals the hot sweeps and hands fields / spins / sweep counters to the warp-per-chain
+    kernel.  Same states as with the hand-over switched off (flag bit 6), for any threshold (bits 16..23: 1 % = the tile
+    kernel does everything, 100 % = it hands over after its first sweep), partial tiles, two problems with their own
+    schedules, host initial states -- and equal to the replay oracle."""
+    Qs = np.stack([random_qubo(n, seed=400 + n + b, scale=1.0 + b) for b in range(2)])
+    h, J, _ = qbm.ising.qubo_to_ising(Qs)
+    betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
+    J32, h32, b32 = J.astype(np.float32), h.astype(np.float32), betas.astype(np.float32)
+    args = [torch.from_numpy(a).to(cuda) for a in (J32, h32, b32)]
+    init = np.stack([qbm.ising.initial_states_numpy(3 + b, reads, n) for b in range(2)])
+    for initd in (None, torch.from_numpy(init).to(cuda)):
+        two = qbm.sa_sample(*args, spb, reads, 31, chain_offset=9, init_states=initd, count=True, flags=pct << 16)
+        one = qbm.sa_sample(*args, spb, reads, 31, chain_offset=9, init_states=initd, count=True, flags=64)
+        assert torch.equal(two.states, one.states)
+        assert torch.equal(two.accepted, one.accepted)          # accepted flips and proposals add up over the two kernels
+    got = two.states.cpu().numpy()
+    ref, _ = oracle.replay_sample(J32[1], h32[1], b32[1], spb, 31, 9 + reads, 2, init01=init[1][:2])
+    assert np.array_equal(got[1][:2], ref)
+
+
 @pytest.mark.parametrize("n", [900, 1290, 1650, 1792])
 def test_kernels_agree_where_their_row_layouts_differ(qbm, cuda, n):
     """8..14 windows: the default kernel stores rows rotated by their own window, the chain-tile and chains-per-warp kernels
