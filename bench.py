@@ -181,7 +181,9 @@ def run_gpu(args):
     bd = torch.from_numpy(betas.astype(np.float32)).to(dev)
     Qd = torch.from_numpy(Q).to(dev)
     L = qbm_b200._lib.load()
-    ws = torch.empty((L.qbm_sa_workspace_bytes(n, 1) + 3) // 4, dtype=torch.float32, device=dev)
+    # the larger workspace enables the library's two-phase schedule (chain-tile kernel for the hot sweeps, then one warp
+    # per chain), which is what sa_sample / B200SASampler use as well
+    ws = torch.empty((L.qbm_sa_workspace_bytes_two_phase(n, 1, R) + 3) // 4, dtype=torch.float32, device=dev)
     out = torch.empty((1, R, n), dtype=torch.int8, device=dev)
     counters = torch.zeros(2, dtype=torch.int64, device=dev)
     launches = [0]
@@ -199,7 +201,7 @@ def run_gpu(args):
         qbm_b200._lib.check(rc)
         e = qbm_b200.qubo_energies(Qd, out)
         if timed:
-            launches[0] += 3          # sa_permute_kernel, sa_kernel, qubo_energy_kernel
+            launches[0] += 4          # sa_permute_kernel, sa_tile_kernel (hot sweeps), sa_kernel, qubo_energy_kernel
             kern_ms.append((ev0, ev1))
         return e
 
@@ -300,10 +302,13 @@ def run_gpu(args):
         except (OSError, ValueError):
             pass
         roofline = {
-            "kernel": "sa_kernel<16,4,16,1>", "bound": "l1-shared-pipe",
-            "bound_note": "neither of the contract's two rooflines applies: the sampler streams coupling rows through the "
-                          "L1/shared data pipe (ncu: l1tex data-pipe 76 %, DRAM 0.001 %, no tensor work); the HBM figures "
-                          "are reported under 'hbm', the FP32 pipe under 'fp32'",
+            "kernel": "sa_tile_kernel<8,384> (hot sweeps) + sa_kernel<16,4,16,1,...,RS> (rest): one qbm_sa_sample launch",
+            "bound": "l1-shared-pipe",
+            "bound_note": "neither of the contract's two rooflines applies: the sampler consumes one coupling row per accepted "
+                          "flip on chip (ncu of the warp-per-chain kernel: l1tex data pipe 78 %, DRAM 0.001 %, no tensor "
+                          "work); 'achieved' counts the ALGORITHMIC bytes 4nA + 4P of SURVEY.md 8d, of which the chain-tile "
+                          "kernel really moves 1/16 in the hot sweeps (one row fetch serves 16 chains), so the fraction is "
+                          "against what one warp per chain would have to stream through L1; HBM under 'hbm', FP32 under 'fp32'",
             "achieved": achieved, "peak": l1_peak,
             "unit": "GB/s", "frac": achieved / l1_peak, "traffic": traffic,
             "peak_source": f"derived: 128 B/clk/SM x {sm_count} SMs x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
