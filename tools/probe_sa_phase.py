@@ -1,5 +1,6 @@
 """Time the first S sweeps of the default 1000-sweep schedule (the hot phase, where nearly every proposal is accepted) for
-different kernels (flag words), n = 2048: G spin-updates/s, accepted fraction and clocks per accepted flip per SM."""
+different kernels (flag words: 64 = warp-per-chain kernel alone, 16 = chain-tile kernel, 32 = chains-per-warp kernel, 0 = the
+default, i.e. the two-phase schedule at n > 1792): G spin-updates/s, accepted fraction and clocks per accepted flip per SM."""
 import argparse
 import os
 import sys
@@ -15,7 +16,7 @@ def main():
     ap.add_argument("--n", type=int, default=2048)
     ap.add_argument("--reads", type=int, default=2368)
     ap.add_argument("--cuts", default="50,100,150,200,300,1000")
-    ap.add_argument("--flags", default="0,16")
+    ap.add_argument("--flags", default="64,16,0")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(19)
