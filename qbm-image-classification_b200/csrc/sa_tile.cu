@@ -30,7 +30,9 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int T = 16;             // chains per CTA
 constexpr int XLD = 36;           // row stride of the transpose buffer
-constexpr int RB = 8;             // ring slots (coupling rows in flight per CTA)
+constexpr int GR = 4;             // coupling rows per ring slot: one full / empty hand-shake per GR rows
+constexpr int NGS = 4;            // ring slots
+constexpr int RB = GR * NGS;      // coupling rows in flight per CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -116,8 +118,8 @@ struct TileSmem {
     uint32_t *rec_old;  // [2][T]
     uint32_t *rec_meta; // [2][4]     union of the flip masks, number of flips, candidate flag
     uint32_t *work;     // [2][4]     producer work item: union, first row, exit flag
-    uint64_t *full;     // [RB]
-    uint64_t *empty;    // [RB]
+    uint64_t *full;     // [NGS]
+    uint64_t *empty;    // [NGS]
     uint64_t *work_full;// [2]
 };
 
@@ -125,7 +127,7 @@ __host__ __device__ inline size_t tile_smem_bytes(int ld)
 {
     const int WIN = ld / 128;
     size_t b = (size_t)RB * ld * 4 + 32 * 32 * 4 + T * XLD * 4 + 4 * 32 * T * 4 + 2 * 32 * T * 4 + (size_t)4 * WIN * T * 4 +
-               2 * T * 4 * 2 + 2 * 4 * 4 * 2 + (size_t)(2 * RB + 2) * 8;
+               2 * T * 4 * 2 + 2 * 4 * 4 * 2 + (size_t)(2 * NGS + 2) * 8;
     return b + 128;
 }
 
@@ -144,8 +146,8 @@ __device__ __forceinline__ TileSmem carve(uint8_t *base, int ld)
     s.rec_old = reinterpret_cast<uint32_t *>(p); p += 2 * T * 4;
     s.rec_meta = reinterpret_cast<uint32_t *>(p); p += 2 * 4 * 4;
     s.work = reinterpret_cast<uint32_t *>(p); p += 2 * 4 * 4;
-    s.full = reinterpret_cast<uint64_t *>(p); p += (size_t)RB * 8;
-    s.empty = reinterpret_cast<uint64_t *>(p); p += (size_t)RB * 8;
+    s.full = reinterpret_cast<uint64_t *>(p); p += (size_t)NGS * 8;
+    s.empty = reinterpret_cast<uint64_t *>(p); p += (size_t)NGS * 8;
     s.work_full = reinterpret_cast<uint64_t *>(p);
     return s;
 }
@@ -168,23 +170,30 @@ struct RowRegs {
     float4 c[T / 4];
 };
 
+// rows of a record come in groups of GR per ring slot; `gi` counts groups since launch, `k` rows of this record.
+// `rel` = the slot to hand back to the producer after this row has been applied (the last row of its group), else NONE
+constexpr uint32_t NONE = 0xffffffffu;
 template <int NS>
-__device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uint32_t &u, uint32_t &ri, uint32_t cb_par, uint32_t &slot,
-                                          bool dense)
+__device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uint32_t &u, uint32_t &gi, uint32_t &k, uint32_t cb_par,
+                                          uint32_t &rel, bool dense)
 {
     const int a = __ffs(u) - 1;
     u &= u - 1;
-    slot = ri & (RB - 1);
-    mbar_wait_s(A.full + slot * 8u, (ri / RB) & 1u);
+    const uint32_t j = k & (GR - 1);
+    const uint32_t slot = gi & (NGS - 1);
+    if (j == 0) mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
 #pragma unroll
-    for (int jw = 0; jw < NS / 4; ++jw) R.r[jw] = lds128(A.ring + slot * A.slot_stride + jw * A.win_stride);
+    for (int jw = 0; jw < NS / 4; ++jw) R.r[jw] = lds128(A.ring + (slot * GR + j) * A.slot_stride + jw * A.win_stride);
     if (dense) {
 #pragma unroll
         for (int q = 0; q < T / 4; ++q) R.c[q] = lds128(cb_par + (uint32_t)a * (T * 4u) + q * 16u);
     } else {
         R.c[0].x = __int_as_float(a);
     }
-    ++ri;
+    ++k;
+    const bool last = (j == GR - 1) || (u == 0u);
+    rel = last ? slot : NONE;
+    if (last) { ++gi; k = 0; }
 }
 
 template <int NS>
@@ -224,27 +233,31 @@ __device__ __forceinline__ void row_apply_sparse(float2 (&F2)[NS / 2][T], const 
 
 template <int NS>
 __device__ __forceinline__ void apply_record(float2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, int par,
-                                             int lane, uint32_t &ri, uint32_t dense_min)
+                                             int lane, uint32_t &gi, uint32_t dense_min)
 {
     const uint32_t cb_par = A.cbuf + (uint32_t)par * (32u * T * 4u);
     RowRegs<NS> Ra, Rb;
-    uint32_t sa, sb;
+    uint32_t sa, sb, k = 0;
     if (count >= dense_min) {
         // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2};
         // two register buffers: the loads of the next row are in flight while the FMAs of this row issue
-        row_fetch<NS>(Ra, A, u, ri, cb_par, sa, true);
+        row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, true);
         while (true) {
             const bool more_b = u != 0u;
-            if (more_b) row_fetch<NS>(Rb, A, u, ri, cb_par, sb, true);
+            if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_par, sb, true);
             row_apply_dense<NS>(F2, Ra);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
+            if (sa != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
+            }
             if (!more_b) break;
             const bool more_a = u != 0u;
-            if (more_a) row_fetch<NS>(Ra, A, u, ri, cb_par, sa, true);
+            if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, true);
             row_apply_dense<NS>(F2, Rb);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
+            if (sb != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
+            }
             if (!more_a) break;
         }
     } else {
@@ -257,19 +270,23 @@ __device__ __forceinline__ void apply_record(float2 (&F2)[NS / 2][T], const Tile
             fl[4 * q] = f4.x; fl[4 * q + 1] = f4.y; fl[4 * q + 2] = f4.z; fl[4 * q + 3] = f4.w;
             ol[4 * q] = o4.x; ol[4 * q + 1] = o4.y; ol[4 * q + 2] = o4.z; ol[4 * q + 3] = o4.w;
         }
-        row_fetch<NS>(Ra, A, u, ri, cb_par, sa, false);
+        row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, false);
         while (true) {
             const bool more_b = u != 0u;
-            if (more_b) row_fetch<NS>(Rb, A, u, ri, cb_par, sb, false);
+            if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_par, sb, false);
             row_apply_sparse<NS>(F2, Ra, fl, ol);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
+            if (sa != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
+            }
             if (!more_b) break;
             const bool more_a = u != 0u;
-            if (more_a) row_fetch<NS>(Ra, A, u, ri, cb_par, sa, false);
+            if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, false);
             row_apply_sparse<NS>(F2, Rb, fl, ol);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
+            if (sb != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
+            }
             if (!more_a) break;
         }
     }
@@ -285,12 +302,16 @@ __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *_
         const uint32_t row0 = sm.work[(kq & 1u) * 4 + 1];
         if (sm.work[(kq & 1u) * 4 + 2]) break;
         while (u) {
-            const int a = __ffs(u) - 1;
-            u &= u - 1;
-            const uint32_t slot = ri & (RB - 1);
-            mbar_wait(&sm.empty[slot], ((ri / RB) & 1u) ^ 1u);
-            mbar_expect_tx(&sm.full[slot], (uint32_t)ld * 4u);
-            bulk_g2s(sm.ring + (size_t)slot * ld, Jp + (size_t)(row0 + a) * (size_t)ld, (uint32_t)ld * 4u, &sm.full[slot]);
+            // one ring slot = up to GR rows of this record, one expect_tx for all of them
+            const uint32_t slot = ri & (NGS - 1);
+            const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
+            mbar_wait(&sm.empty[slot], ((ri / NGS) & 1u) ^ 1u);
+            mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)ld * 4u);
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const int a = __ffs(u) - 1;
+                u &= u - 1;
+                bulk_g2s(sm.ring + (size_t)(slot * GR + j) * ld, Jp + (size_t)(row0 + a) * (size_t)ld, (uint32_t)ld * 4u, &sm.full[slot]);
+            }
             ++ri;
         }
         ++kq;
@@ -318,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     const float *__restrict__ Jp = p.Jp + (size_t)q * (size_t)n * (size_t)ld;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < RB; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], (uint32_t)W); }
+        for (int i = 0; i < NGS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], (uint32_t)W); }
         mbar_init(&sm.work_full[0], 1);
         mbar_init(&sm.work_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
