@@ -135,7 +135,9 @@ __device__ __forceinline__ TileSmem carve(uint8_t *base, int ld)
 {
     const int WIN = ld / 128;
     TileSmem s;
-    uint8_t *p = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(base) + 127) & ~uintptr_t(127));
+    // `base` is the 128-byte aligned dynamic shared memory: every address below is base + a constant, which lets the
+    // compiler fold the shared-space addresses of the row loop instead of re-deriving an aligned base in it
+    uint8_t *p = base;
     s.ring = reinterpret_cast<float *>(p); p += (size_t)RB * ld * 4;
     s.Dbuf = reinterpret_cast<float *>(p); p += 32 * 32 * 4;
     s.Xbuf = reinterpret_cast<float *>(p); p += T * XLD * 4;
@@ -325,7 +327,7 @@ __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *_
 template <int NS, int NTHREADS>
 __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, const int W, const int ctas_per_problem)
 {
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int n = p.n, ld = p.ld;
