@@ -86,7 +86,7 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *                bit 5: use the multi-chain warp kernel (a warp anneals 2-4 chains of one problem and shares their
  *                       coupling-row loads; identical trajectories, n > 128 and num_reads >= 2 only)
  *                bit 6: never use the two-phase schedule; bits 16..23: its hand-over threshold in percent of
- *                       accepted proposals per sweep (0 = default 75)
+ *                       accepted proposals per sweep (0 = default 70)
  *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed
  *                       by TMA through a shared-memory ring; identical trajectories);
  *                       bits 8..15: its dense/sparse update switch in percent of flipped (chain, variable)
