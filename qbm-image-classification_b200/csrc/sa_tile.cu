@@ -17,12 +17,17 @@
 //                  shared memory.  Output: per chain a flip mask, the old spins and a coefficient matrix
 //       update     all warps: for every flipped variable a (in sweep order) the row J[a] is read once
 //                  from the ring and applied to all chains that flipped a: F[.][t] = fma(c_t, J[a][.], F[.][t])
-//   * a producer warp feeds the ring: one cp.async.bulk (TMA, 1-D) per coupling row, mbarrier
-//     full/empty handshakes; rows come from L2 (the matrix is read once per sweep and SM, not once per
-//     flip and chain)
+//   * a producer warp feeds the ring: one cp.async.bulk (TMA, 1-D) per coupling row, one mbarrier
+//     full/empty hand-shake per ring slot of GR rows; rows come from L2 (the matrix is read once per sweep
+//     and SM, not once per flip and chain)
 //
 // Every field element receives exactly the FMA sequence of the sequential rule, in the same order, so
 // the final states are bit-identical to the replay oracle (tests/test_gpu_sa.py).
+//
+// Use: as a whole-schedule sampler behind qbm_sa_sample flag bit 4, and -- by default for n > 1792 -- for the
+// hot sweeps of the two-phase schedule: with hot_fraction > 0 the kernel stops after the first sweep that accepts
+// less than that fraction of its proposals and exports fields (in the warp kernel's register layout), spins and
+// the number of completed sweeps, from which sa_warp.cuh's resuming instantiation continues (sa_kernel.cu).
 #include "sa_common.cuh"
 
 namespace {
