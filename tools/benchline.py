@@ -1,3 +1,4 @@
+"""Pretty-print the headline fields of bench.py JSON lines read from stdin: python bench.py | python tools/benchline.py"""
 import json, sys
 for ln in sys.stdin:
     ln = ln.strip()

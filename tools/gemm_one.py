@@ -1,3 +1,4 @@
+"""One warm launch of the TF32 tcgen05 GEMM at a square size (for an ncu capture): python tools/gemm_one.py 8192"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, qbm_b200
