@@ -281,10 +281,9 @@ class SampleSet:
         return SampleSet(self.record[keep], self.variables, dict(self.info), self.vartype)
 
     def aggregate(self):
-        rows, inv, cnt = np.unique(self.record.sample, axis=0, return_inverse=True, return_counts=True)
+        rows, first_idx, inv = np.unique(self.record.sample, axis=0, return_index=True, return_inverse=True)
         inv = np.asarray(inv).reshape(-1)
-        first_idx = np.array([np.flatnonzero(inv == k)[0] for k in range(rows.shape[0])], dtype=int)
-        occ = np.array([self.record.num_occurrences[inv == k].sum() for k in range(rows.shape[0])], dtype=np.intc)
+        occ = np.bincount(inv, weights=self.record.num_occurrences, minlength=rows.shape[0]).astype(np.intc)
         out = SampleSet.from_samples(rows, self.record.energy[first_idx], self.vartype, info=self.info,
                                      num_occurrences=occ)
         out.variables = list(self.variables)

@@ -87,6 +87,14 @@ def test_dimod_shim_boundary_types(qbm):
     assert ss.record.num_occurrences.tolist() == [1, 1, 1]
     agg = dimod.SampleSet.from_samples(np.array([[1, 0], [1, 0], [0, 1]]), [1.0, 1.0, 2.0], "BINARY").aggregate()
     assert sorted(agg.record.num_occurrences.tolist()) == [1, 2]
+    big = np.random.default_rng(3).integers(0, 2, (5000, 6)).astype(np.int8)      # 64 distinct rows, many repeats
+    agg = dimod.SampleSet.from_samples(big, big.sum(1).astype(float), "BINARY", num_occurrences=np.full(5000, 2)).aggregate()
+    assert len(agg) == len(np.unique(big, axis=0)) and int(agg.record.num_occurrences.sum()) == 10000
+    assert np.array_equal(agg.record.energy, agg.record.sample.sum(1))
+    low = ss.lowest()
+    assert len(low) == 1 and low.record.sample.tolist() == [[0, 0, 0]]
+    assert [d.energy for d in ss.data()] == sorted(ss.record.energy.tolist())
+    assert [d.energy for d in ss.data(sorted_by=None)] == ss.record.energy.tolist()
     np_rows = np.vstack([np.array(list(s.values())) for s in ss.samples()])       # faster_dqbm.py:777-778
     assert np_rows.shape == (3, 3)
     pickle.loads(pickle.dumps(b))
