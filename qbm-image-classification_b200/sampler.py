@@ -46,6 +46,9 @@ def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_
 
     ``J`` float32 [batch_q, n, n] (symmetric, zero diagonal), ``h`` float32 [batch_q, n],
     ``betas`` float32 [batch_q, num_betas] or [1, num_betas] / [num_betas] (shared schedule).
+    ``flags`` is passed to ``qbm_sa_sample`` (include/qbm_b200.h): 0 = the library's choice -- the warp-per-chain kernel,
+    for n > 1792 preceded by the chain-tile kernel over the hot sweeps (two-phase schedule); 64 = never two-phase,
+    16 / 32 = the chain-tile / chains-per-warp kernel for the whole schedule.  Every choice returns the same states.
     """
     L = _lib.load()
     if J.dim() == 2:
