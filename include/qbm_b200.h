@@ -246,6 +246,15 @@ int qbm_convdeep_errors(int P, int num_layers, const int *layer_sizes, int n_lab
 int qbm_test_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out, long long count, void *stream);
 int qbm_test_neg_log(const uint32_t *u, float *out, long long count, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Measurement hook (no reference counterpart): on-chip peaks of the current device, the denominators of the
+ * sampler's rooflines.  Streams FFMA2 / FFMA, conflict-free LDS.128 and L1-hit LDG.128 loops for a
+ * few milliseconds each, timed with CUDA events; SYNCHRONISES `stream`.
+ *   out     host double[4]: fp32 TFLOP/s with fma.rn.f32x2, fp32 TFLOP/s with fma.rn.f32, shared-memory TB/s, L1 TB/s
+ *   scratch device buffer, 16-byte aligned, at least 1 MiB + 16 bytes
+ */
+int qbm_probe_onchip_peaks(double *out, void *scratch, size_t scratch_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

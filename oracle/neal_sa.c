@@ -14,10 +14,14 @@
  *     otherwise accept iff exp(-dE*beta) * (2^64-1) > xorshift128+()
  *   - rng state {seed ? seed : 2^64-1, 0}, continuing across reads
  *   - energy = sum h_i s_i + sum_{couplers} J_ij s_i s_j
- * PARITY STATUS: sample-level parity is UNPINNED (the reference holds no golden sample sets
- * and neal itself is absent); what pins this file is (i) exact identities tested in
+ * PARITY STATUS: sample-level parity with real neal is UNPINNED (the reference holds no golden
+ * sample sets and neal itself is absent); what pins this file is (i) exact identities tested in
  * tests/test_oracle_sa.py (energy bookkeeping, brute-force ground states, detailed balance)
- * and (ii) the reference's recorded accuracies reproduced through it (tests/golden/).
+ * and (ii) reference-held end-to-end answers: all 70 PneumoniaMNIST last-epoch runs with
+ * h in {4..12} (trained weights + recorded accuracy/AUC, out/paper_data/Pneumonia_param_doku)
+ * are annealed THROUGH THIS FILE for every one of the 624 test images and the majority output
+ * bit reproduces the recorded pair exactly
+ * (tests/test_oracle_models.py::test_recorded_accuracy_through_the_neal_restatement_all_70_runs).
  *
  * Build: make -C oracle   (gcc -O2 -shared -fPIC)
  */

@@ -21,8 +21,10 @@ vendored and not installable here, so their published algorithms are restated):
                             linear-only shortcut (:13-17)
 
 PARITY STATUS: sample-level behaviour of neal is "parity unpinned" (no golden sample sets in the
-reference, neal absent); it is pinned end-to-end by tests/golden/ (recorded accuracies of the
-reference's own runs) and by exact identities (tests/test_oracle_sa.py).
+reference, neal absent); ``neal_sample`` is pinned end-to-end by reference-held data -- the 70
+PneumoniaMNIST last-epoch runs (weights + recorded accuracy/AUC) are annealed through it and every
+recorded pair is reproduced exactly (tests/test_oracle_models.py) -- and by exact identities
+(tests/test_oracle_sa.py).
 """
 from __future__ import annotations
 

@@ -1,0 +1,134 @@
+// On-chip peak probes: the denominators of the sampler's rooflines, measured on the device the benchmark runs on
+// instead of derived from data-sheet rates ("derived on-chip peaks to use as denominators
+// until measured on the box").  Three streaming micro-kernels, each timed with CUDA events:
+//   FFMA2 / FFMA  fp32 FMA pipe: 16 independent accumulators per thread, fma.rn.f32x2 or fma.rn.f32
+//   LDS.128       shared-memory data pipe: conflict-free 16-byte loads, every lane a different bank group
+//   LDG.128 (L1)  read-only global loads that hit L1: each CTA re-reads a 16 KB slice
+// Not part of the reference's interface; used by bench.py to report `roofline.peak` as a measured number.
+#include "common.cuh"
+
+namespace {
+
+constexpr int PK_THREADS = 512;
+constexpr int PK_ACC = 16;
+
+template <bool PACKED>
+__global__ void __launch_bounds__(PK_THREADS) peak_fma_kernel(float *out, int iters, float a, float b)
+{
+    float2 acc[PK_ACC];
+#pragma unroll
+    for (int i = 0; i < PK_ACC; ++i) acc[i] = make_float2((float)threadIdx.x + i, (float)i);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < PK_ACC; ++i) {
+            if (PACKED) {
+                asm volatile("fma.rn.f32x2 %0, %0, %1, %2;"
+                             : "+l"(reinterpret_cast<unsigned long long &>(acc[i]))
+                             : "l"(reinterpret_cast<const unsigned long long &>(aa)),
+                               "l"(reinterpret_cast<const unsigned long long &>(bb)));
+            } else {
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i].x) : "f"(a), "f"(b));
+                asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i].y) : "f"(a), "f"(b));
+            }
+        }
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < PK_ACC; ++i) s += acc[i].x + acc[i].y;
+    if (s == 123.456f) out[0] = s;                      // never true: keeps the accumulators alive
+}
+
+__global__ void __launch_bounds__(PK_THREADS) peak_lds_kernel(uint32_t *out, int iters)
+{
+    extern __shared__ __align__(16) uint8_t pk_smem[];
+    constexpr int BYTES = 64 * 1024;
+    for (int i = threadIdx.x; i < BYTES / 4; i += PK_THREADS) reinterpret_cast<uint32_t *>(pk_smem)[i] = i;
+    __syncthreads();
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(pk_smem);
+    uint32_t x = 0, y = 0;
+    uint32_t off = threadIdx.x * 16u;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + off) : "memory");
+            x ^= v.x ^ v.y;
+            y ^= v.z ^ v.w;
+            off = (off + PK_THREADS * 16u) & (BYTES - 1u);
+        }
+    }
+    if ((x ^ y) == 0xdeadbeefu) out[0] = x;
+}
+
+__global__ void __launch_bounds__(PK_THREADS) peak_ldg_kernel(const uint4 *__restrict__ src, uint32_t *out, int iters)
+{
+    constexpr int SLICE = 16 * 1024 / 16;               // uint4 elements each CTA re-reads (stays in L1)
+    const uint4 *p = src + (size_t)(blockIdx.x % 64) * SLICE;
+    uint32_t x = 0, y = 0;
+    uint32_t off = threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            uint4 v;
+            asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + off) : "memory");
+            x ^= v.x ^ v.y;
+            y ^= v.z ^ v.w;
+            off = (off + PK_THREADS) & (SLICE - 1u);
+        }
+    }
+    if ((x ^ y) == 0xdeadbeefu) out[0] = x;
+}
+
+}  // namespace
+
+// out (host) [4]: FFMA2 TFLOP/s, FFMA TFLOP/s, shared-memory LDS.128 TB/s, L1-hit LDG.128 TB/s.
+// `scratch`: device buffer of at least 1 MiB + 16 bytes (16-byte aligned), read by the L1 probe.  Synchronises the stream.
+extern "C" QBM_API int qbm_probe_onchip_peaks(double *out, void *scratch, size_t scratch_bytes, void *stream)
+{
+    QBM_CHECK_ARG(out && scratch, "qbm_probe_onchip_peaks: null pointer argument");
+    QBM_CHECK_ARG(scratch_bytes >= (1u << 20) + 16 && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0,
+                  "qbm_probe_onchip_peaks: scratch must be 16-byte aligned and >= 1 MiB + 16 bytes");
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 0;
+    QBM_CUDA_OK(cudaGetDevice(&dev));
+    QBM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaEvent_t e0, e1;
+    QBM_CUDA_OK(cudaEventCreate(&e0));
+    QBM_CUDA_OK(cudaEventCreate(&e1));
+    const int blocks = sms * 2;
+    float *fout = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(scratch) + (1u << 20));
+    uint32_t *uout = reinterpret_cast<uint32_t *>(fout);
+    QBM_CUDA_OK(cudaFuncSetAttribute(peak_lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    QBM_CUDA_OK(cudaMemsetAsync(scratch, 1, 1u << 20, st));
+
+    auto timed = [&](auto launch, double &ms_out) -> int {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {             // first repetition = warm-up, best of the other three
+            QBM_CUDA_OK(cudaEventRecord(e0, st));
+            launch();
+            QBM_CUDA_OK(cudaEventRecord(e1, st));
+            QBM_CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0.0f;
+            QBM_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && ms < best) best = ms;
+        }
+        QBM_LAUNCH_OK("peak probe");
+        ms_out = best;
+        return QBM_OK;
+    };
+    const int fma_iters = 1 << 14, mem_iters = 1 << 11;
+    double ms = 0.0;
+    int rc;
+    if ((rc = timed([&] { peak_fma_kernel<true><<<blocks, PK_THREADS, 0, st>>>(fout, fma_iters, 1.0000001f, 1e-9f); }, ms))) return rc;
+    out[0] = (double)blocks * PK_THREADS * fma_iters * PK_ACC * 2 * 2.0 / (ms * 1e-3) * 1e-12;
+    if ((rc = timed([&] { peak_fma_kernel<false><<<blocks, PK_THREADS, 0, st>>>(fout, fma_iters, 1.0000001f, 1e-9f); }, ms))) return rc;
+    out[1] = (double)blocks * PK_THREADS * fma_iters * PK_ACC * 2 * 2.0 / (ms * 1e-3) * 1e-12;
+    if ((rc = timed([&] { peak_lds_kernel<<<blocks, PK_THREADS, 64 * 1024, st>>>(uout, mem_iters); }, ms))) return rc;
+    out[2] = (double)blocks * PK_THREADS * mem_iters * 8 * 16.0 / (ms * 1e-3) * 1e-12;
+    if ((rc = timed([&] { peak_ldg_kernel<<<blocks, PK_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(scratch), uout, mem_iters); }, ms))) return rc;
+    out[3] = (double)blocks * PK_THREADS * mem_iters * 8 * 16.0 / (ms * 1e-3) * 1e-12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return QBM_OK;
+}

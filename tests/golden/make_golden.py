@@ -214,6 +214,69 @@ def recorded_accuracy(out):
     np.savez_compressed(out, **d)
 
 
+def recorded_accuracy_all(out):
+    """All 70 PneumoniaMNIST last-epoch runs with h in {4,5,6,7,8,10,12} (10 seeds each; SURVEY.md section 4 found the
+    recorded (accuracy, AUC) of every one of them reproduced by the ground state of the unclamped QUBO).  Per run: the
+    image-independent off-diagonal part of the unclamped QUBO and the per-image diagonal from the reference's own
+    create_qubo_matrix_from, plus the recorded pair.  Diagonals are stored as float32: enough to leave every ground
+    state unchanged (checked here against the float64 QUBO by exact enumeration) at half the fixture size."""
+    import re
+    import src.model.faster_dqbm as Fq
+    from src import data_loader
+    (trX, trY), (vaX, vaY), (teX, teY) = data_loader.get_medmnist("src/data/medmnist/pneumoniamnist.npz")
+    _, teXf, _ = data_loader.preprocess_images(trX[:2], teX)
+    teXf = np.asarray(teXf, dtype=np.float64)
+    labels = np.asarray(teY).astype(np.int8).reshape(-1)
+    d = {"labels": labels}
+    k = 0
+    for h in (4, 5, 6, 7, 8, 10, 12):
+        base = f"out/paper_data/Pneumonia_param_doku/{h}_hnodes"
+        for run in sorted(glob.glob(os.path.join(base, "_se*"))):
+            seed = int(os.path.basename(run).split("_se")[1].split("_")[0])
+            wfiles = glob.glob(os.path.join(run, "e*__*.pkl"))
+            last = max(int(re.match(r"e(\d+)__", os.path.basename(f)).group(1)) for f in wfiles)
+            wfile = [f for f in wfiles if os.path.basename(f).startswith(f"e{last}__")][0]
+            with open(wfile, "rb") as f:
+                W = pickle.load(f)
+            with open(os.path.join(run, "test_val", f"e{last}_h{h}_{seed}_testacc_auc.pkl"), "rb") as f:
+                acc, auc = pickle.load(f)
+            restricted = len(W) == 5
+            m = Fq.Disc_QBM(dim_input=784, num_classes=2, use_one_hot_encoding=False, n_hidden_nodes=h,
+                            restricted=restricted, sample_count=100, anneal_steps=1000, beta_eff=1.0, parallelize=False,
+                            seed=seed)
+            if restricted:
+                (m.weights_all_visible_to_hidden, m.weights_clamped_visible_to_output, m.biases_hidden, m.biases_output,
+                 m.weights_output_output) = W
+            else:
+                (m.weights_all_visible_to_hidden, m.weights_clamped_visible_to_output, m.biases_hidden, m.biases_output,
+                 m.weights_output_output, m.weights_hidden_hidden) = W
+            n = h + 1
+            Q0 = m.create_qubo_matrix_from(teXf[0])
+            off = Q0 - np.diag(np.diag(Q0))
+            # the diagonal of every image in one product, checked against the reference's builder on a few images
+            lin = np.concatenate([np.ravel(m.biases_output), np.ravel(m.biases_hidden)])[None, :] + teXf @ np.concatenate(
+                [m.weights_clamped_visible_to_output, m.weights_all_visible_to_hidden[1:]], axis=1)
+            lin = lin / m.beta_eff
+            for i in (0, 1, 311, 623):
+                Q = m.create_qubo_matrix_from(teXf[i])
+                assert np.array_equal(Q - np.diag(np.diag(Q)), off)
+                assert np.allclose(np.diag(Q), lin[i], rtol=1e-12, atol=1e-12), (h, seed, i)
+            diag32 = lin.astype(np.float32)
+            X = ((np.arange(2 ** n)[:, None] >> np.arange(n)) & 1).astype(np.float64)
+            quad = np.einsum("ri,ij,rj->r", X, off, X)
+            gs64 = np.argmin(lin @ X.T + quad[None], axis=1)
+            gs32 = np.argmin(diag32.astype(np.float64) @ X.T + quad[None], axis=1)
+            assert np.array_equal(gs64, gs32), (h, seed)
+            pred = (gs64 & 1).astype(int)
+            assert abs(np.mean(pred == labels) - acc) < 1e-12, (h, seed, np.mean(pred == labels), acc)
+            d[f"off_{k}"] = off; d[f"diag_{k}"] = diag32; d[f"acc_{k}"] = acc; d[f"auc_{k}"] = auc
+            d[f"seed_{k}"] = seed; d[f"h_{k}"] = h; d[f"epoch_{k}"] = last
+            d[f"sc_{k}"] = int(re.search(r"_sc(\d+)_", os.path.basename(run)).group(1))     # the run's sample count
+            k += 1
+    d["num_runs"] = k
+    np.savez_compressed(out, **d)
+
+
 def main():
     with ref_stubs.reference_imports():
         disc_qbm_loop(os.path.join(HERE, "disc_qbm_loop_onehot.npz"))
@@ -222,6 +285,7 @@ def main():
         convdeep(os.path.join(HERE, "convdeep_onehot.npz"), one_hot=True)
         rbm(os.path.join(HERE, "rbm_discriminative.npz"))
         recorded_accuracy(os.path.join(HERE, "pneumonia_h10_recorded_accuracy.npz"))
+        recorded_accuracy_all(os.path.join(HERE, "pneumonia_last_epoch_recorded_accuracy.npz"))
     for f in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
         print(f"{os.path.basename(f):45s} {os.path.getsize(f) / 1024:8.1f} KB")
 

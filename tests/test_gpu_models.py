@@ -112,6 +112,24 @@ def test_recorded_accuracy_through_the_gpu_sampler(qbm, cuda):
         assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12
 
 
+def test_recorded_accuracy_all_70_pneumonia_runs_through_the_gpu_sampler(qbm, cuda):
+    """The same 70 reference-held (weights, recorded accuracy/AUC) pairs that pin the CPU restatement of neal
+    (tests/test_oracle_models.py::test_recorded_accuracy_through_the_neal_restatement_all_70_runs), through the product:
+    per run one batched launch of 624 unclamped QUBOs with the run's own sample count and 1000 sweeps."""
+    from sklearn.metrics import roc_auc_score
+    g = np.load(os.path.join(G, "pneumonia_last_epoch_recorded_accuracy.npz"))
+    labels = g["labels"].astype(int)
+    assert int(g["num_runs"]) == 70
+    for k in range(70):
+        off, diag = g[f"off_{k}"], g[f"diag_{k}"].astype(np.float64)
+        Q = off[None] + np.stack([np.diag(d) for d in diag])
+        smp, _, _ = qbm.sample_qubo_batch(Q, int(g[f"sc_{k}"]), 1000, seed=int(g[f"seed_{k}"]) % (2 ** 32), return_energy=False)
+        pred = np.round(smp[:, :, 0].mean(axis=1)).astype(int)
+        tag = (k, int(g[f"h_{k}"]), int(g[f"seed_{k}"]))
+        assert abs(np.mean(pred == labels) - float(g[f"acc_{k}"])) < 1e-12, tag
+        assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12, tag
+
+
 def _golden_params(g, prefix):
     return {k: g[f"{prefix}_{k}"] for k in ("W_vh", "W_vo", "W_oo", "b_h", "b_o", "W_hh")}
 

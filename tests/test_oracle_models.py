@@ -119,3 +119,41 @@ def test_recorded_accuracy_by_exact_enumeration():
         pred = np.array([int(X[np.argmin(X @ d + quad), 0]) for d in diag])
         assert abs(np.mean(pred == labels) - float(g[f"acc_{k}"])) < 1e-12
         assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12
+
+
+def _majority_predictions_of_run(args):
+    """Worker (forked process): Disc_QBM.predict for every test image of one recorded run through oracle.neal_sample."""
+    from oracle import oracle as O
+    off, diag, seed, sc = args
+    pred = np.empty(len(diag), dtype=int)
+    for i, d in enumerate(diag):
+        smp, _ = O.neal_sample(off + np.diag(d), 30, 1000, seed=seed)
+        if 0.2 < smp[:, 0].mean() < 0.8:
+            smp, _ = O.neal_sample(off + np.diag(d), sc, 1000, seed=seed)
+        pred[i] = int(np.round(smp[:, 0].mean()))                        # predict(): np.round(mean of the output column)
+    return pred
+
+
+def test_recorded_accuracy_through_the_neal_restatement_all_70_runs(oracle):
+    """Pins oracle/neal_sa.c + the dimod/neal glue of oracle.py to data the reference holds: for all 70 PneumoniaMNIST
+    last-epoch runs with h in {4,5,6,7,8,10,12} (out/paper_data/Pneumonia_param_doku/<h>_hnodes/_se*/)
+    the unclamped QUBO of every one of the 624 test images is annealed by ``oracle.neal_sample`` -- the restated
+    ``neal.SimulatedAnnealingSampler().sample(bqm, num_reads, num_sweeps=1000, seed=run seed)`` -- and the majority output
+    bit over the reads (Disc_QBM.predict, faster_dqbm.py:1227-1241) must give exactly the (accuracy, AUC) the reference
+    recorded for that run.  To keep the CPU suite short an image is first annealed with 30 reads; only when that vote is
+    not decisive (output mean within (0.2, 0.8): near-degenerate ground states, a handful of images) it is re-annealed
+    with the run's own sample count (50..600, from the run's parameter string).  The schedule is the runs' 1000 sweeps."""
+    import multiprocessing as mp
+    from sklearn.metrics import roc_auc_score
+    g = load("pneumonia_last_epoch_recorded_accuracy.npz")
+    labels = g["labels"].astype(int)
+    runs = int(g["num_runs"])
+    assert runs == 70
+    jobs = [(g[f"off_{k}"], g[f"diag_{k}"].astype(np.float64), int(g[f"seed_{k}"]) % (2 ** 32), int(g[f"sc_{k}"]))
+            for k in range(runs)]
+    with mp.get_context("fork").Pool(min(os.cpu_count() or 4, 16)) as pool:
+        preds = pool.map(_majority_predictions_of_run, jobs, chunksize=1)
+    for k, pred in enumerate(preds):
+        tag = (k, int(g[f"h_{k}"]), int(g[f"seed_{k}"]))
+        assert abs(float(np.mean(pred == labels)) - float(g[f"acc_{k}"])) < 1e-12, tag
+        assert abs(float(roc_auc_score(labels, pred)) - float(g[f"auc_{k}"])) < 1e-12, tag
