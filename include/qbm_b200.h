@@ -245,6 +245,11 @@ int qbm_convdeep_errors(int P, int num_layers, const int *layer_sizes, int n_lab
  */
 int qbm_test_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out, long long count, void *stream);
 int qbm_test_neg_log(const uint32_t *u, float *out, long long count, void *stream);
+/*   qbm_rbm_workspace_layout: offsets (in floats, host long long[12]) of the step intermediates inside the RBM workspace,
+ *   in this order: A [B,ld4(H)], P [B,ld4(C)], Dt [H,ld4(B)], xt [V,ld4(B)], p0 [B,ld4(H)], p0t [H,ld4(B)], h0 [B,ld4(H)],
+ *   v1 [B,ld4(V)], v1t [V,ld4(B)], p1t [H,ld4(B)], pc [B,ld4(C)], y1 int32[B] -- after qbm_rbm_cd1_step they hold ph0, the
+ *   draws h0 / v1 / y1, p(y|h0) and ph1^T, which tests/test_gpu_rbm.py replays against oracle.rbm_cd1_step_replay */
+int qbm_rbm_workspace_layout(int B, int V, int H, int C, long long *offsets);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hook (no reference counterpart): on-chip peaks of the current device, the denominators of the

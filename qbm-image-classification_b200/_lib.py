@@ -60,6 +60,7 @@ SIGNATURES = {
                                    _c_p, _c_p, _c_p, _c_p]),
     "qbm_test_philox": (_c_i, [_c_p, _c_p, _c_p, _c_ll, _c_p]),
     "qbm_test_neg_log": (_c_i, [_c_p, _c_p, _c_ll, _c_p]),
+    "qbm_rbm_workspace_layout": (_c_i, [_c_i, _c_i, _c_i, _c_i, _c_p]),
     "qbm_probe_onchip_peaks": (_c_i, [_c_p, _c_p, _c_sz, _c_p]),
 }
 

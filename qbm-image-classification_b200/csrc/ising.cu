@@ -178,6 +178,10 @@ extern "C" QBM_API int qbm_qubo_to_ising(const double *Q, int n, long long batch
     QBM_CHECK_ARG(Q && J_out && h_out, "qbm_qubo_to_ising: null pointer argument");
     QBM_CHECK_ARG(n >= 1 && batch >= 1, "qbm_qubo_to_ising: n and batch must be >= 1");
     QBM_CHECK_ARG(batch <= 0x7fffffffLL, "qbm_qubo_to_ising: batch too large");
+    if (n > 4096) {       // the pairwise-summation leaf table (MAX_LEAVES = 64 leaves of <= 128 elements) covers n <= 4096 only
+        qbm_set_error("qbm_qubo_to_ising: n=%d exceeds the 4096 variables the row-sum kernel is built for", n);
+        return QBM_EUNSUPPORTED;
+    }
     qubo_to_ising_kernel<<<(unsigned)batch, WARPS * 32, 0, (cudaStream_t)stream>>>(Q, n, J_out, h_out, offset, range);
     QBM_LAUNCH_OK("qubo_to_ising_kernel");
     return QBM_OK;

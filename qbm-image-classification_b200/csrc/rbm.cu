@@ -301,6 +301,18 @@ extern "C" QBM_API size_t qbm_rbm_workspace_bytes(int B, int V, int H, int C)
     return ws_floats(B, V, H, C) * sizeof(float);
 }
 
+// test hook: float offsets of the step intermediates inside the workspace, so that tests can replay the CD-1 draws
+extern "C" QBM_API int qbm_rbm_workspace_layout(int B, int V, int H, int C, long long *offsets)
+{
+    if (int rc = check_dims("qbm_rbm_workspace_layout", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(offsets, "qbm_rbm_workspace_layout: null pointer argument");
+    const Ws w = carve(nullptr, B, V, H, C);
+    const float *base = nullptr;
+    const float *ptrs[12] = {w.A, w.P, w.Dt, w.xt, w.p0, w.p0t, w.h0, w.v1, w.v1t, w.p1t, w.pc, reinterpret_cast<float *>(w.y1)};
+    for (int i = 0; i < 12; ++i) offsets[i] = (long long)(ptrs[i] - base);
+    return QBM_OK;
+}
+
 // R1 (:43-47): P[B, ld4(H)] = sigmoid(v.W + b_h + U[y]);  Wt = W^T [H, ld4(V)]
 extern "C" QBM_API int qbm_rbm_sample_hidden(const float *Wt, const float *U, const float *b_h, const float *v, const int *y,
                                              int B, int V, int H, int C, float *P, void *stream)

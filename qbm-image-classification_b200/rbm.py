@@ -86,9 +86,18 @@ class B200ClassificationRBM:
 
     @weights.setter
     def weights(self, w):
-        w = torch.as_tensor(w, dtype=torch.float32).to(self.device)
+        # the getter returns a view of the padded storage, so `m.weights += d` (the reference's own update_weights
+        # pattern, ClassificationRBM.py:88-99) hands that view back: copy before touching the storage
+        w = torch.as_tensor(w, dtype=torch.float32).to(self.device).clone()
+        if w.shape != (self.num_visible, self.num_hidden):
+            raise ValueError(f"weights must be [{self.num_visible}, {self.num_hidden}], got {tuple(w.shape)}")
         self._W.zero_(); self._W[:, :self.num_hidden] = w
-        self._Wt.zero_(); self._Wt[:, :self.num_visible] = w.t()
+        self.sync_transposed_weights()
+
+    def sync_transposed_weights(self):
+        """Rebuild the K-major copy W^T the GEMMs read from W (needed after in-place edits through the ``weights`` view,
+        e.g. ``m.weights.add_(d)``; the setter and the step functions do it themselves)."""
+        self._Wt.zero_(); self._Wt[:, :self.num_visible] = self._W[:, :self.num_hidden].t()
 
     @property
     def class_weights(self):
@@ -96,7 +105,10 @@ class B200ClassificationRBM:
 
     @class_weights.setter
     def class_weights(self, u):
-        self._U.zero_(); self._U[:, :self.num_hidden] = torch.as_tensor(u, dtype=torch.float32).to(self.device)
+        u = torch.as_tensor(u, dtype=torch.float32).to(self.device).clone()
+        if u.shape != (self.num_classes, self.num_hidden):
+            raise ValueError(f"class_weights must be [{self.num_classes}, {self.num_hidden}], got {tuple(u.shape)}")
+        self._U.zero_(); self._U[:, :self.num_hidden] = u
 
     # ---- helpers ------------------------------------------------------------------------------------
     def _workspace(self, B):

@@ -70,6 +70,14 @@ def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_
     num_betas = betas.shape[1]
     beta_stride = 0 if betas.shape[0] == 1 else num_betas
     dev = J.device
+    if num_betas == 0:
+        # neal with num_sweeps = 0 returns the initial states: nothing to anneal, so nothing to launch
+        if init_states is None:
+            raise ValueError("sa_sample: an empty schedule needs explicit init_states (there is nothing to anneal)")
+        if init_states.shape != (bq, num_reads, n) or init_states.dtype != torch.int8:
+            raise ValueError("sa_sample: init_states must be int8 [batch_q, num_reads, n]")
+        states = init_states.contiguous().clone() if out is None else out.copy_(init_states)
+        return SAResult(states=states, accepted=torch.zeros(2, dtype=torch.int64, device=dev) if count else None)
     # the larger workspace lets the library run its two-phase schedule where that is faster (n > 1792)
     need = L.qbm_sa_workspace_bytes_two_phase(n, bq, int(num_reads))
     if workspace is None or workspace.numel() * workspace.element_size() < need:
@@ -147,6 +155,8 @@ def qubo_to_ising_device(Q: torch.Tensor):
         raise ValueError("qubo_to_ising_device: Q must be a CUDA float64 tensor")
     Q = Q.contiguous()
     B, n, _ = Q.shape
+    if n > 4096:
+        raise ValueError(f"qubo_to_ising_device: n={n} exceeds the 4096 variables the row-sum kernel is built for")
     dev = Q.device
     J = torch.empty((B, n, n), dtype=torch.float32, device=dev)
     h = torch.empty((B, n), dtype=torch.float32, device=dev)
@@ -176,7 +186,8 @@ def _all_gather_reads(local: torch.Tensor, num_reads: int, group) -> torch.Tenso
 
 def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, seed=None, beta_range=None,
                       beta_schedule_type: str = "geometric", initial_states_generator: str = "numpy",
-                      device=None, return_energy: bool = True, chain_offset: int = 0, process_group=None):
+                      device=None, return_energy: bool = True, chain_offset: int = 0, process_group=None,
+                      src_rank: int | None = None):
     """Sample a batch of dense QUBOs ``[B, n, n]`` (float64, host).  Host logic (spin conversion, beta
     range, schedule, initial states) follows neal/dimod in float64 (:mod:`ising`); the annealing, the
     energies and nothing else run on the GPU.
@@ -184,6 +195,9 @@ def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, see
     With ``process_group`` (one process per GPU) the reads are sharded over the ranks -- rank r anneals the
     contiguous block ``dist.shard_range(num_reads, world, r)`` keyed by the global read index, so the result does not
     depend on the number of GPUs -- and all-gathered, so that every rank returns all ``num_reads`` samples in read order.
+    A ``seed`` of None is drawn on rank 0 and broadcast, so that the shards belong to one reproducible call.  With
+    ``src_rank`` the problem is taken from that rank only: its ``Q`` is broadcast over the group on the device (NCCL; 33.6 MB
+    of float64 at n = 2048) and the ``Q`` the other ranks pass is used for its shape alone.
 
     Returns ``(samples int8 [B, R, n] numpy, energies float64 [B, R] numpy or None, info dict)``.
     """
@@ -196,14 +210,23 @@ def sample_qubo_batch(Q: np.ndarray, num_reads: int, num_sweeps: int = 1000, see
     seed = ising.check_seed(seed)
     if seed is None:
         seed = int(np.random.randint(2 ** 31))
+        if process_group is not None:
+            import torch.distributed as dist
+            box = [seed]
+            dist.broadcast_object_list(box, src=dist.get_global_rank(process_group, 0), group=process_group)
+            seed = int(box[0])
     # BINARY -> SPIN and the two reductions of neal's beta rule run on the device (K0 reproduces the float64 host
     # formulas of ising.py bit for bit, numpy's summation order included); the schedule itself is built on the host from
     # those two numbers exactly as neal does (np.geomspace)
     Qd = torch.from_numpy(Q).to(dev)
+    if process_group is not None and src_rank is not None:
+        import torch.distributed as dist
+        dist.broadcast(Qd, src=dist.get_global_rank(process_group, int(src_rank)), group=process_group)
     Jd, hd, off_d, rng_d = qubo_to_ising_device(Qd)
-    offset = off_d.cpu().numpy()
+    host3 = torch.cat([off_d[:, None], rng_d], dim=1).cpu().numpy()       # one device->host copy for offset + both reductions
+    offset = host3[:, 0].copy()
     if beta_range is None:
-        r = rng_d.cpu().numpy()
+        r = host3[:, 1:]
         br = ising.beta_range_from_reductions(r[:, 0], r[:, 1])
     else:
         br = np.broadcast_to(np.asarray(beta_range, dtype=np.float64), (B, 2))

@@ -71,6 +71,7 @@ class SimulatedAnnealingSampler:
         betas, spb = ising.beta_schedule(br, int(num_sweeps), beta_schedule_type)
         if init is None:
             init = ising.initial_states_numpy(seed, int(num_reads), n)
+        # num_sweeps = 0: neal returns the initial states with their energies (sa_sample short-circuits the empty schedule)
         res = _sampler.sa_sample(torch.from_numpy(J.astype(np.float32)).to(dev), torch.from_numpy(h.astype(np.float32)).to(dev),
                                  torch.from_numpy(betas.astype(np.float32)).to(dev), spb, int(num_reads), seed,
                                  init_states=torch.from_numpy(np.ascontiguousarray(init)[None]).to(dev))

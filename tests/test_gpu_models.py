@@ -58,6 +58,10 @@ def test_neal_dimod_shims_end_to_end(qbm, oracle, cuda):
         assert np.allclose(sp.record.energy.min(), -1.3)
         sq = SimulatedAnnealingSampler().sample_qubo({(0, 0): -1.0, (1, 1): -1.0, (0, 1): 3.0}, num_reads=8, num_sweeps=50, seed=3)
         assert np.isclose(sq.record.energy.min(), -1.0)
+        # num_sweeps = 0: neal returns the initial states (dimod's RandomState(seed) draw) with their energies
+        s0 = SimulatedAnnealingSampler().sample(bqm, num_reads=6, num_sweeps=0, seed=5)
+        assert np.array_equal(s0.record.sample, qbm.ising.initial_states_numpy(5, 6, 21))
+        assert np.allclose(s0.record.energy, oracle.qubo_energies(Q, s0.record.sample), rtol=1e-12, atol=1e-12)
     finally:
         qbm.shims.uninstall()
 

@@ -160,6 +160,97 @@ def test_rbm_cd1_step_statistics(qbm, cuda):
     assert torch.equal(m2.weights, m.weights) and torch.equal(m2.class_bias, m.class_bias)
 
 
+def test_rbm_weight_setters_do_not_alias_their_own_storage(qbm, cuda):
+    """`m.weights += d` / `m.weights = m.weights` (the reference's update_weights pattern, ClassificationRBM.py:88-99) hand
+    the getter's view back to the setter; W, W^T and U must come out updated, not zeroed."""
+    m = qbm.B200ClassificationRBM(30, 18, 1, num_classes=3, learning_rate=0.1, seed=2)
+    m.class_weights = torch.randn(3, 18)
+    W0, U0 = m.weights.clone(), m.class_weights.clone()
+    m.weights = m.weights
+    m.class_weights = m.class_weights
+    assert torch.equal(m.weights, W0) and torch.equal(m.class_weights, U0)
+    d = torch.randn(30, 18, device=cuda)
+    m.weights += d
+    m.class_weights *= 0.5
+    assert torch.equal(m.weights, W0 + d) and torch.equal(m.class_weights, U0 * 0.5)
+    assert torch.equal(m._Wt[:, :30], m._W[:, :18].t())
+    m.weights.add_(1.0)                                     # in-place through the view: W^T needs an explicit refresh
+    m.sync_transposed_weights()
+    assert torch.equal(m._Wt[:, :30], (W0 + d + 1.0).t())
+    with pytest.raises(ValueError):
+        m.weights = torch.zeros(18, 30)
+
+
+def _cd1_intermediates(qbm, m, B):
+    """Views of the CD-1 intermediates the step leaves in the model's workspace (qbm_rbm_workspace_layout)."""
+    import ctypes
+    V, H, C = m.num_visible, m.num_hidden, m.num_classes
+    off = (ctypes.c_longlong * 12)()
+    qbm._lib.check(qbm._lib.load().qbm_rbm_workspace_layout(B, V, H, C, off))
+    ld4 = lambda c: (c + 3) & ~3
+    ws = m._ws
+
+    def mat(i, rows, cols):
+        return ws[off[i]:off[i] + rows * ld4(cols)].view(rows, ld4(cols))[:, :cols].cpu().numpy()
+
+    y1 = ws[off[11]:off[11] + B].view(torch.int32).cpu().numpy().astype(np.int64)
+    return dict(p0=mat(4, B, H), h0=mat(6, B, H), v1=mat(7, B, V), p1t=mat(9, H, B), pc=mat(10, B, C), y1=y1)
+
+
+@pytest.mark.parametrize("V,H,C,B", [(784, 500, 10, 256), (64, 48, 4, 32), (130, 70, 7, 50)])
+def test_rbm_cd1_step_replays_the_kernel_draws(qbm, cuda, V, H, C, B):
+    """CD-1 replay oracle (oracle/model_oracle.py::rbm_cd1_step_replay: the composition of ClassificationRBM.py:43-60 that
+    SURVEY.md section 8a specifies, in float64, fed the kernel's own Philox streams (seed, step*4 + stream)):
+      * ph0, p(y|h0), ph1 equal the oracle's probabilities at TF32 tolerance
+      * every Bernoulli / categorical draw the kernel made is the draw its OWN probability and the Philox uniform imply,
+        exactly (h0 against the exported ph0, y1 against the exported p(y|h0)); v1, whose probabilities stay inside the GEMM
+        epilogue, equals the oracle's draw from float64 probabilities everywhere except where |u - p| is inside the TF32
+        error band, and the whole trajectory (h0, v1, y1) equals the float64 replay except inside such bands
+      * the parameter update equals R5 applied to the kernel's own phase samples at TF32 tolerance."""
+    rng = np.random.default_rng(V + B)
+    lr, seed = 0.1, 0x1234567812345
+    m = qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=lr, seed=seed)
+    m.class_weights = torch.from_numpy((rng.standard_normal((C, H)) * 0.05).astype(np.float32))
+    m.hidden_bias = torch.from_numpy((rng.standard_normal(H) * 0.1).astype(np.float32)).to(cuda)
+    m.class_bias = torch.from_numpy((rng.standard_normal(C) * 0.1).astype(np.float32)).to(cuda)
+    v0 = (rng.random((B, V)) < 0.3).astype(np.float32)
+    y0 = rng.integers(0, C, B)
+    tol = 4e-3                                               # TF32 operands: |p_gpu - p_f64| band around a uniform
+    for step in range(2):
+        W, U = m.weights.cpu().numpy().astype(np.float64), m.class_weights.cpu().numpy().astype(np.float64)
+        bv, bh, bc = (t.cpu().numpy().astype(np.float64) for t in (m.visible_bias, m.hidden_bias, m.class_bias))
+        assert m._step == step
+        m.cd1_training(torch.from_numpy(v0), torch.from_numpy(y0))
+        torch.cuda.synchronize()
+        k = _cd1_intermediates(qbm, m, B)
+        new, o = M.rbm_cd1_step_replay(W, U, bv, bh, bc, v0, y0, lr, seed, step)
+        # positive phase and its draw
+        assert np.abs(k["p0"] - o["ph0"]).max() < tol
+        assert np.array_equal(k["h0"], (o["uh"] < k["p0"]).astype(np.float32)), "h0 is not the draw of the kernel's own ph0"
+        band_h = np.abs(o["uh"] - o["ph0"]) < tol
+        assert np.array_equal(k["h0"][~band_h], o["h0"][~band_h].astype(np.float32)) and band_h.mean() < 0.02
+        # negative phase, conditioned on the kernel's h0 (identical to the replay's unless a draw fell inside a band)
+        h0 = k["h0"].astype(np.float64)
+        pv1 = M.rbm_sample_visible(W, bv, h0)
+        band_v = np.abs(o["uv"] - pv1) < tol
+        assert np.array_equal(k["v1"][~band_v], (o["uv"] < pv1)[~band_v].astype(np.float32)) and band_v.mean() < 0.02
+        pc = M.rbm_sample_class(U, bc, h0)
+        assert np.abs(k["pc"] - pc).max() < tol
+        assert np.array_equal(k["y1"], M.rbm_categorical_draw(k["pc"], o["uc"])), "y1 is not the draw of the kernel's own p(y|h0)"
+        v1, y1 = k["v1"].astype(np.float64), k["y1"]
+        ph1 = M.rbm_sample_hidden(W, U, bh, v1, np.eye(C)[y1])
+        assert np.abs(k["p1t"].T - ph1).max() < tol
+        if not band_h.any():                                 # no draw near a band: the whole trajectory is the float64 replay
+            assert np.array_equal(h0, o["h0"])
+        # parameter update from the kernel's own samples (R5)
+        ref = M.rbm_cd1_update(W, U, bv, bh, bc, v0.astype(np.float64), y0, k["p0"].astype(np.float64), v1, y1, ph1, lr)
+        assert np.allclose(m.weights.cpu().numpy(), ref["W"], rtol=0, atol=3e-4)
+        assert np.allclose(m.class_weights.cpu().numpy(), ref["U"], rtol=0, atol=3e-4)
+        assert np.allclose(m.visible_bias.cpu().numpy(), ref["b_v"], rtol=0, atol=1e-5)
+        assert np.allclose(m.hidden_bias.cpu().numpy(), ref["b_h"], rtol=0, atol=3e-4)
+        assert np.allclose(m.class_bias.cpu().numpy(), ref["b_c"], rtol=0, atol=1e-5)
+
+
 def test_train_rbm_epoch_loop(qbm, cuda):
     """ClassificationRBM.train_rbm (src/ClassificationRBM.py:159-205): loader of (batch, labels) pairs, returns
     (loss_list, model, nll_list); the loss falls and the test accuracy beats chance on separable synthetic data."""
