@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(PK_THREADS) peak_lds_kernel(uint32_t *out, int
             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(base + off) : "memory");
             x ^= v.x ^ v.y;
             y ^= v.z ^ v.w;
-            off = (off + PK_THREADS * 16u) & (BYTES - 1u);
+            off = (off + PK_THREADS * 16u + 16u) & (BYTES - 1u);     // long period: ptxas must not merge the loads of an unrolled body
         }
     }
     if ((x ^ y) == 0xdeadbeefu) out[0] = x;
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(PK_THREADS) peak_ldg_kernel(const uint4 *__res
             asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p + off) : "memory");
             x ^= v.x ^ v.y;
             y ^= v.z ^ v.w;
-            off = (off + PK_THREADS) & (SLICE - 1u);
+            off = (off + PK_THREADS + 1u) & (SLICE - 1u);
         }
     }
     if ((x ^ y) == 0xdeadbeefu) out[0] = x;

@@ -1,43 +1,50 @@
-// K1b: simulated-annealing QUBO sampler for sm_100a -- a register tile of 16 chains per CTA.
+// K1b: simulated-annealing QUBO sampler for sm_100a -- a register tile of 16 chains per CTA, software-pipelined.
 //
-// Same trajectory as sa_kernel.cu (oracle/replay_sa.c), different execution.  In
-// the hot part of neal's legacy schedule nearly every proposal is accepted (acceptance > 0.9 for the
-// first ~10 % of the sweeps, where ~97 % of all flips happen), so every chain needs nearly every
-// coupling row in every sweep.  One warp per chain streams a row per flip per chain through L1 (the
-// 128 B/clk/SM pipe is the wall).  Here the 16 chains of a CTA advance in lock-step over 32-variable
-// sub-windows and each coupling row is fetched ONCE for all of them:
+// Same trajectory as sa_kernel.cu (oracle/replay_sa.c), different execution.  In the hot part of
+// neal's legacy schedule nearly every proposal is accepted (acceptance > 0.9 for the first ~10 % of the sweeps, where
+// ~97 % of all flips happen), so every chain needs nearly every coupling row in every sweep.  One warp per chain streams
+// a row per flip per chain through L1 (the 128 B/clk/SM pipe is the wall).  Here the 16 chains of a CTA advance in
+// lock-step over 32-variable sub-windows, each coupling row is fetched ONCE for all of them, and the inherently serial
+// part (deciding the 32 proposals of a sub-window in sweep order) runs one sub-window AHEAD of the field updates on a
+// warp of its own, so the FMA pipe never waits for it.  Warp roles of a CTA (384 threads, one CTA per SM):
 //
-//   * fields: thread (warp w, lane l) holds NS columns x 16 chains in registers (column = variable
-//     (jw*W + w)*128 + k*32 + l, i.e. lane-aligned sub-windows of the 128-variable windows warp w owns)
-//   * per sub-window s (32 consecutive variables, owned by one warp):
-//       pre-check  owner, lane = variable: can any chain accept anything here (dE < 44.36142/beta)?
-//       bounds     all warps: Philox + -ln(u)/beta for the 128-variable window, once per window and sweep
-//       scan       owner, lane = chain (16 chains x 2 halves): the 32 variables are visited in sweep order;
-//                  a flip updates the 32 fields of the sub-window from the 32x32 diagonal block of J in
-//                  shared memory.  Output: per chain a flip mask, the old spins and a coefficient matrix
-//       update     all warps: for every flipped variable a (in sweep order) the row J[a] is read once
-//                  from the ring and applied to all chains that flipped a: F[.][t] = fma(c_t, J[a][.], F[.][t])
-//   * a producer warp feeds the ring: one cp.async.bulk (TMA, 1-D) per coupling row, one mbarrier
-//     full/empty hand-shake per ring slot of GR rows; rows come from L2 (the matrix is read once per sweep
-//     and SM, not once per flip and chain)
+//   appliers  warps 0..W-1 (two warpgroups, registers raised with setmaxnreg): thread (warp w, lane l) holds NS columns
+//             x 16 chains of local fields in registers (column = variable (jw*W + w)*128 + k*32 + l).  They consume
+//             RECORDS in order: for every flipped variable a of a record (sweep order) the row J[a] is read once from
+//             the ring and applied to all chains that flipped a: F[.][t] = fma(c_t, J[a][.], F[.][t]) (FFMA2).  Before
+//             applying record r the owner of sub-window r+1 exports that sub-window's 32 x 16 fields to shared memory.
+//   scanner   warp 9, lane = chain x half: takes the exported fields of sub-window r+1 (they contain every flip up to
+//             record r-1), applies record r to them itself from the 32x32 block J[rows of r][columns of r+1] -- the same
+//             FMAs in the same order as the appliers will -- then visits the 32 variables in sweep order (a flip
+//             updates the 32 fields from the diagonal block) and publishes record r+1: per chain a flip mask, the old
+//             spins and a coefficient matrix c[a][t] in {0, +-2}.  Spins live with the scanner only.
+//   bounds    warp 10: Philox + -ln(u)/beta acceptance bounds of the next 128-variable window, double-buffered
+//   producer  warp 8, one lane: one cp.async.bulk (TMA, 1-D) per flipped coupling row into a ring of 16 rows, one
+//             mbarrier full/empty hand-shake per ring slot of 4 rows; rows come from L2 (the matrix is read once per
+//             sweep and SM, not once per flip and chain)
 //
-// Every field element receives exactly the FMA sequence of the sequential rule, in the same order, so
-// the final states are bit-identical to the replay oracle (tests/test_gpu_sa.py).
+// All hand-offs (records, field exports, bounds, ring slots) are mbarrier full/empty pairs; there is no CTA-wide
+// barrier inside the sweep loop.  Every field element receives exactly the FMA sequence of the sequential rule, in the
+// same order, so the final states are bit-identical to the replay oracle (tests/test_gpu_sa.py).
 //
-// Use: as a whole-schedule sampler behind qbm_sa_sample flag bit 4, and -- by default for n > 1792 -- for the
-// hot sweeps of the two-phase schedule: with hot_fraction > 0 the kernel stops after the first sweep that accepts
-// less than that fraction of its proposals and exports fields (in the warp kernel's register layout), spins and
-// the number of completed sweeps, from which sa_warp.cuh's resuming instantiation continues (sa_kernel.cu).
+// Use: as a whole-schedule sampler behind qbm_sa_sample flag bit 4, and -- by default for large n -- for the hot sweeps
+// of the two-phase schedule: with hot_fraction > 0 the kernel stops after the first sweep that accepts less than that
+// fraction of its proposals and exports fields (in the warp kernel's register layout), spins and the number of
+// completed sweeps, from which sa_warp.cuh's resuming instantiation continues (sa_kernel.cu).
 #include "sa_common.cuh"
 
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int T = 16;             // chains per CTA
-constexpr int XLD = 36;           // row stride of the transpose buffer
 constexpr int GR = 4;             // coupling rows per ring slot: one full / empty hand-shake per GR rows
 constexpr int NGS = 4;            // ring slots
 constexpr int RB = GR * NGS;      // coupling rows in flight per CTA
+constexpr int NREC = 4;           // record buffers (the scanner runs at most one sub-window ahead of the slowest applier)
+constexpr int FXLD = 32 * T + 32; // floats per field-export buffer: [column][chain], the upper 16 columns shifted by 16
+constexpr int NTHREADS = 384;
+constexpr int WARP_PRODUCER = 8, WARP_SCANNER = 9, WARP_BOUNDS = 10;
+constexpr int REGS_APPLIER = 208, REGS_HELPER = 88;      // 2 * 208 + 88 = 504 = 3 * 168 (the launch allocation)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -97,92 +104,101 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid
     const int sz = valid ? 4 : 0;                           // src-size 0: zero fill
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ float4 lds128(uint32_t saddr)
 {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ uint4 lds128u(uint32_t saddr)
-{
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
-    return v;
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+// appliers + scanner (the warps that touch the spin words): start-up and write-back rendezvous only
+__device__ __forceinline__ void tile_sync(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
 struct TileSmem {
-    float *ring;        // [RB][ld]
-    float *Dbuf;        // [32][32]   diagonal block of the current sub-window (natural order)
-    float *Xbuf;        // [T][XLD]   transpose buffer
-    float *bounds;      // [4][32][T] acceptance bounds of the current 128-variable window
-    float *Cbuf;        // [2][32][T] update coefficients of the record
-    uint32_t *spinw;    // [4*WIN][T] spins, one word per (sub-window, chain)
-    uint32_t *rec_flip; // [2][T]
-    uint32_t *rec_old;  // [2][T]
-    uint32_t *rec_meta; // [2][4]     union of the flip masks, number of flips, candidate flag
-    uint32_t *work;     // [2][4]     producer work item: union, first row, exit flag
-    uint64_t *full;     // [NGS]
-    uint64_t *empty;    // [NGS]
-    uint64_t *work_full;// [2]
+    float *ring;         // [RB][ld]
+    float *Dbuf;         // [2][64][32]  rows 0..31: J[rows of the previous sub-window][columns of this one], 32..63: diagonal block
+    float *Fx;           // [2][FXLD]    exported fields of the sub-window the scanner visits next
+    float *bounds;       // [2][4][32][T] acceptance bounds of a 128-variable window
+    float *Cbuf;         // [NREC][32][T][2] update coefficients of a record, each stored twice: (c, c) is an FFMA2 operand
+    uint32_t *spinw;     // [MAXSUB][T]  spins, one word per (sub-window, chain)
+    uint32_t *rowmask;   // [NREC][32]   per flipped variable: chains that flipped it (bits 0..15), their old spins (bits 16..31)
+    uint32_t *rec_meta;  // [NREC][4]    union of the flip masks, number of flips, first row, exit flag
+    uint32_t *ctl;       // [4]          [0] exit flag for the bounds warp
+    uint64_t *full;      // [NGS]  ring slot filled (producer -> appliers)
+    uint64_t *empty;     // [NGS]  ring slot released (appliers -> producer)
+    uint64_t *rec_full;  // [NREC] record published (scanner -> appliers, producer)
+    uint64_t *rec_empty; // [NREC] record consumed (appliers, producer -> scanner)
+    uint64_t *fx_full;   // [2]    fields exported (owning applier -> scanner)
+    uint64_t *fx_empty;  // [2]
+    uint64_t *bnd_full;  // [2]    bounds drawn (bounds warp -> scanner)
+    uint64_t *bnd_empty; // [2]
 };
 
-__host__ __device__ inline size_t tile_smem_bytes(int ld)
-{
-    const int WIN = ld / 128;
-    size_t b = (size_t)RB * ld * 4 + 32 * 32 * 4 + T * XLD * 4 + 4 * 32 * T * 4 + 2 * 32 * T * 4 + (size_t)4 * WIN * T * 4 +
-               2 * T * 4 * 2 + 2 * 4 * 4 * 2 + (size_t)(2 * NGS + 2) * 8;
-    return b + 128;
-}
+// layout: every small buffer at a compile-time offset from the (128-byte aligned) dynamic shared memory base, the ring --
+// the only part whose size depends on n -- last; all shared addresses of the control path fold to base + immediate
+constexpr int MAXSUB = QBM_SA_MAX_N / 32;             // sub-windows of the largest problem
+constexpr size_t OFF_DBUF = 0;
+constexpr size_t OFF_FX = OFF_DBUF + 2 * 64 * 32 * 4;
+constexpr size_t OFF_BOUNDS = OFF_FX + 2 * FXLD * 4;
+constexpr size_t OFF_CBUF = OFF_BOUNDS + 2 * 4 * 32 * T * 4;
+constexpr size_t OFF_SPINW = OFF_CBUF + NREC * 32 * T * 8;
+constexpr size_t OFF_ROWMASK = OFF_SPINW + (size_t)MAXSUB * T * 4;
+constexpr size_t OFF_META = OFF_ROWMASK + NREC * 32 * 4;
+constexpr size_t OFF_CTL = OFF_META + NREC * 4 * 4;
+constexpr size_t OFF_BARS = OFF_CTL + 4 * 4;
+constexpr size_t OFF_RING = (OFF_BARS + (size_t)(2 * NGS + 2 * NREC + 8) * 8 + 127) / 128 * 128;
 
-__device__ __forceinline__ TileSmem carve(uint8_t *base, int ld)
+__host__ __device__ inline size_t tile_smem_bytes(int ld) { return OFF_RING + (size_t)RB * ld * 4; }
+
+__device__ __forceinline__ TileSmem carve(uint8_t *base)
 {
-    const int WIN = ld / 128;
     TileSmem s;
-    // `base` is the 128-byte aligned dynamic shared memory: every address below is base + a constant, which lets the
-    // compiler fold the shared-space addresses of the row loop instead of re-deriving an aligned base in it
-    uint8_t *p = base;
-    s.ring = reinterpret_cast<float *>(p); p += (size_t)RB * ld * 4;
-    s.Dbuf = reinterpret_cast<float *>(p); p += 32 * 32 * 4;
-    s.Xbuf = reinterpret_cast<float *>(p); p += T * XLD * 4;
-    s.bounds = reinterpret_cast<float *>(p); p += 4 * 32 * T * 4;
-    s.Cbuf = reinterpret_cast<float *>(p); p += 2 * 32 * T * 4;
-    s.spinw = reinterpret_cast<uint32_t *>(p); p += (size_t)4 * WIN * T * 4;
-    s.rec_flip = reinterpret_cast<uint32_t *>(p); p += 2 * T * 4;
-    s.rec_old = reinterpret_cast<uint32_t *>(p); p += 2 * T * 4;
-    s.rec_meta = reinterpret_cast<uint32_t *>(p); p += 2 * 4 * 4;
-    s.work = reinterpret_cast<uint32_t *>(p); p += 2 * 4 * 4;
-    s.full = reinterpret_cast<uint64_t *>(p); p += (size_t)NGS * 8;
-    s.empty = reinterpret_cast<uint64_t *>(p); p += (size_t)NGS * 8;
-    s.work_full = reinterpret_cast<uint64_t *>(p);
+    s.Dbuf = reinterpret_cast<float *>(base + OFF_DBUF);
+    s.Fx = reinterpret_cast<float *>(base + OFF_FX);
+    s.bounds = reinterpret_cast<float *>(base + OFF_BOUNDS);
+    s.Cbuf = reinterpret_cast<float *>(base + OFF_CBUF);
+    s.spinw = reinterpret_cast<uint32_t *>(base + OFF_SPINW);
+    s.rowmask = reinterpret_cast<uint32_t *>(base + OFF_ROWMASK);
+    s.rec_meta = reinterpret_cast<uint32_t *>(base + OFF_META);
+    s.ctl = reinterpret_cast<uint32_t *>(base + OFF_CTL);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + OFF_BARS);
+    s.full = bars; s.empty = bars + NGS;
+    s.rec_full = bars + 2 * NGS; s.rec_empty = bars + 2 * NGS + NREC;
+    s.fx_full = bars + 2 * NGS + 2 * NREC; s.fx_empty = s.fx_full + 2;
+    s.bnd_full = s.fx_full + 4; s.bnd_empty = s.fx_full + 6;
+    s.ring = reinterpret_cast<float *>(base + OFF_RING);
     return s;
 }
 
-// ---- update: apply the flips of record `par` to every field this thread holds ----------------------
-// rows arrive through the ring in ascending order of the flipped variable; `ri` counts rows since launch.
-// Fields are kept as float2 pairs (two adjacent sub-windows of a lane) so that one FFMA2 updates two of them.
+// ---- appliers: apply the flips of a record to every field this thread holds --------------------------
+// rows arrive through the ring in ascending order of the flipped variable.  Fields are kept as float2 pairs (two
+// adjacent sub-windows of a lane) so that one FFMA2 updates two of them.
 struct TileAddr {          // shared-space byte addresses, computed once per thread
     uint32_t ring;         // this thread's float4 of window 0 in ring slot 0
     uint32_t slot_stride;  // ld * 4
     uint32_t win_stride;   // W * 512
     uint32_t cbuf;         // Cbuf[0][0][0]
-    uint32_t full, empty;  // barrier arrays
-    uint32_t flip, old;    // rec_flip[0], rec_old[0]
+    uint32_t full, empty;  // ring barrier arrays
+    uint32_t rowmask;      // rowmask[0][0]
 };
 
 template <int NS>
 struct RowRegs {
     float4 r[NS / 4];
-    float4 c[T / 4];
+    uint32_t c;            // dense: shared address of the row's coefficient pairs; sparse: the row's mask word
 };
 
 // rows of a record come in groups of GR per ring slot; `gi` counts groups since launch, `k` rows of this record.
 // `rel` = the slot to hand back to the producer after this row has been applied (the last row of its group), else NONE
 constexpr uint32_t NONE = 0xffffffffu;
 template <int NS>
-__device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uint32_t &u, uint32_t &gi, uint32_t &k, uint32_t cb_par,
-                                          uint32_t &rel, bool dense)
+__device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uint32_t &u, uint32_t &gi, uint32_t &k, uint32_t cb_rec,
+                                          uint32_t rm_rec, uint32_t &rel, bool dense)
 {
     const int a = __ffs(u) - 1;
     u &= u - 1;
@@ -191,12 +207,8 @@ __device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uin
     if (j == 0) mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
 #pragma unroll
     for (int jw = 0; jw < NS / 4; ++jw) R.r[jw] = lds128(A.ring + (slot * GR + j) * A.slot_stride + jw * A.win_stride);
-    if (dense) {
-#pragma unroll
-        for (int q = 0; q < T / 4; ++q) R.c[q] = lds128(cb_par + (uint32_t)a * (T * 4u) + q * 16u);
-    } else {
-        R.c[0].x = __int_as_float(a);
-    }
+    if (dense) R.c = cb_rec + (uint32_t)a * (T * 8u);
+    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(R.c) : "r"(rm_rec + (uint32_t)a * 4u));
     ++k;
     const bool last = (j == GR - 1) || (u == 0u);
     rel = last ? slot : NONE;
@@ -206,28 +218,29 @@ __device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uin
 template <int NS>
 __device__ __forceinline__ void row_apply_dense(float2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
+    // coefficients come as ready (c, c) pairs, two chains per 128-bit load (warp-uniform address: a broadcast)
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-        const float4 c4 = R.c[t >> 2];
-        const float c = (t & 3) == 0 ? c4.x : ((t & 3) == 1 ? c4.y : ((t & 3) == 2 ? c4.z : c4.w));
-        const float2 cc = make_float2(c, c);
+    for (int t2 = 0; t2 < T / 2; ++t2) {
+        const float4 c4 = lds128(R.c + (uint32_t)t2 * 16u);
+        const float2 ca = make_float2(c4.x, c4.y), cb = make_float2(c4.z, c4.w);
 #pragma unroll
         for (int jw = 0; jw < NS / 4; ++jw) {
-            ffma2(F2[jw * 2 + 0][t], cc, make_float2(R.r[jw].x, R.r[jw].y));
-            ffma2(F2[jw * 2 + 1][t], cc, make_float2(R.r[jw].z, R.r[jw].w));
+            ffma2(F2[jw * 2 + 0][2 * t2], ca, make_float2(R.r[jw].x, R.r[jw].y));
+            ffma2(F2[jw * 2 + 1][2 * t2], ca, make_float2(R.r[jw].z, R.r[jw].w));
+            ffma2(F2[jw * 2 + 0][2 * t2 + 1], cb, make_float2(R.r[jw].x, R.r[jw].y));
+            ffma2(F2[jw * 2 + 1][2 * t2 + 1], cb, make_float2(R.r[jw].z, R.r[jw].w));
         }
     }
 }
 
 template <int NS>
-__device__ __forceinline__ void row_apply_sparse(float2 (&F2)[NS / 2][T], const RowRegs<NS> &R, const uint32_t (&fl)[T],
-                                                 const uint32_t (&ol)[T])
+__device__ __forceinline__ void row_apply_sparse(float2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
-    const int a = __float_as_int(R.c[0].x);
+    const uint32_t m = R.c;              // bits 0..15: chains that flipped this variable, bits 16..31: their old spins
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        if ((fl[t] >> a) & 1u) {
-            const float c = ((ol[t] >> a) & 1u) ? -2.0f : 2.0f;
+        if ((m >> t) & 1u) {             // warp-uniform
+            const float c = ((m >> (16 + t)) & 1u) ? -2.0f : 2.0f;
             const float2 cc = make_float2(c, c);
 #pragma unroll
             for (int jw = 0; jw < NS / 4; ++jw) {
@@ -239,75 +252,52 @@ __device__ __forceinline__ void row_apply_sparse(float2 (&F2)[NS / 2][T], const 
 }
 
 template <int NS>
-__device__ __forceinline__ void apply_record(float2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, int par,
+__device__ __forceinline__ void apply_record(float2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, uint32_t rb,
                                              int lane, uint32_t &gi, uint32_t dense_min)
 {
-    const uint32_t cb_par = A.cbuf + (uint32_t)par * (32u * T * 4u);
+    const uint32_t cb_rec = A.cbuf + rb * (32u * T * 8u);
+    const uint32_t rm_rec = A.rowmask + rb * (32u * 4u);
     RowRegs<NS> Ra, Rb;
     uint32_t sa, sb, k = 0;
-    if (count >= dense_min) {
-        // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2};
-        // two register buffers: the loads of the next row are in flight while the FMAs of this row issue
-        row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, true);
-        while (true) {
-            const bool more_b = u != 0u;
-            if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_par, sb, true);
-            row_apply_dense<NS>(F2, Ra);
-            if (sa != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
-            }
-            if (!more_b) break;
-            const bool more_a = u != 0u;
-            if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, true);
-            row_apply_dense<NS>(F2, Rb);
-            if (sb != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
-            }
-            if (!more_a) break;
+    // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2};
+    // sparse: per chain a warp-uniform test of the row's mask word.
+    // Two register buffers: the loads of the next row are in flight while the FMAs of this row issue
+    const bool dense = count >= dense_min;
+    row_fetch<NS>(Ra, A, u, gi, k, cb_rec, rm_rec, sa, dense);
+    while (true) {
+        const bool more_b = u != 0u;
+        if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_rec, rm_rec, sb, dense);
+        if (dense) row_apply_dense<NS>(F2, Ra);
+        else row_apply_sparse<NS>(F2, Ra);
+        if (sa != NONE) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
         }
-    } else {
-        // sparse: per chain a warp-uniform test of its flip mask
-        uint32_t fl[T], ol[T];
-#pragma unroll
-        for (int q = 0; q < T / 4; ++q) {
-            const uint4 f4 = lds128u(A.flip + (uint32_t)par * (T * 4u) + q * 16u);
-            const uint4 o4 = lds128u(A.old + (uint32_t)par * (T * 4u) + q * 16u);
-            fl[4 * q] = f4.x; fl[4 * q + 1] = f4.y; fl[4 * q + 2] = f4.z; fl[4 * q + 3] = f4.w;
-            ol[4 * q] = o4.x; ol[4 * q + 1] = o4.y; ol[4 * q + 2] = o4.z; ol[4 * q + 3] = o4.w;
+        if (!more_b) break;
+        const bool more_a = u != 0u;
+        if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_rec, rm_rec, sa, dense);
+        if (dense) row_apply_dense<NS>(F2, Rb);
+        else row_apply_sparse<NS>(F2, Rb);
+        if (sb != NONE) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
         }
-        row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, false);
-        while (true) {
-            const bool more_b = u != 0u;
-            if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_par, sb, false);
-            row_apply_sparse<NS>(F2, Ra, fl, ol);
-            if (sa != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
-            }
-            if (!more_b) break;
-            const bool more_a = u != 0u;
-            if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_par, sa, false);
-            row_apply_sparse<NS>(F2, Rb, fl, ol);
-            if (sb != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
-            }
-            if (!more_a) break;
-        }
+        if (!more_a) break;
     }
 }
 
-// ---- producer: one bulk copy (TMA, 1-D) per requested coupling row -----------------------------------
+// ---- producer: one bulk copy (TMA, 1-D) per flipped coupling row of every record ---------------------
 __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *__restrict__ Jp, int ld)
 {
-    uint32_t kq = 0, ri = 0;
+    uint32_t r = 0, ri = 0;
     while (true) {
-        mbar_wait(&sm.work_full[kq & 1u], (kq >> 1) & 1u);
-        uint32_t u = sm.work[(kq & 1u) * 4 + 0];
-        const uint32_t row0 = sm.work[(kq & 1u) * 4 + 1];
-        if (sm.work[(kq & 1u) * 4 + 2]) break;
+        const uint32_t rb = r & (NREC - 1);
+        mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u);
+        uint32_t u = sm.rec_meta[rb * 4 + 0];
+        const uint32_t row0 = sm.rec_meta[rb * 4 + 2];
+        const uint32_t ex = sm.rec_meta[rb * 4 + 3];
+        mbar_arrive(&sm.rec_empty[rb]);
+        if (ex) break;
         while (u) {
             // one ring slot = up to GR rows of this record, one expect_tx for all of them
             const uint32_t slot = ri & (NGS - 1);
@@ -321,15 +311,260 @@ __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *_
             }
             ++ri;
         }
-        ++kq;
+        ++r;
     }
 }
 
-// NS == 8 (n > 1024): 384 threads = two consumer warpgroups (warps 0..W-1 work) + one producer warpgroup
-// (warp 8 lane 0 works); registers are moved from the producer to the consumer warpgroups with setmaxnreg
-// so that the 128 field registers + working set of a consumer fit without spilling.
-// NS == 4 (n <= 1024): (W + 1) warps, the last one is the producer.
-template <int NS, int NTHREADS>
+// ---- bounds warp: min(thr, -ln(u/2^32)/beta) for every (variable, chain) of the next window -------------
+__device__ __forceinline__ void tile_bounds(const TileSmem &sm, const SaParams &p, const float *__restrict__ betas,
+                                            unsigned long long chain0, int lane)
+{
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    const int nwin = (p.n + 127) >> 7;
+    volatile uint32_t *ctl = sm.ctl;
+    uint32_t wi = 0, t_sweep = 0;
+    for (int b = 0; b < p.num_betas; ++b) {
+        const float beta = __ldg(betas + b);
+        const float thr = __fdiv_rn(44.36142f, beta);
+        for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++t_sweep) {
+            for (int g = 0; g < nwin; ++g, ++wi) {
+                const uint32_t buf = wi & 1u;
+                mbar_wait(&sm.bnd_empty[buf], ((wi >> 1) & 1u) ^ 1u);
+                if (ctl[0] != 0u) return;
+                float *bo = sm.bounds + buf * (4 * 32 * T);
+#pragma unroll 2
+                for (int task = lane; task < 32 * T; task += 32) {
+                    const int tc = task % T, ln = task / T;
+                    const unsigned long long chain = chain0 + (unsigned long long)tc;
+                    const Philox4 o = philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), t_sweep, (uint32_t)(g * 32 + ln), k0, k1);
+                    const uint32_t us[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) bo[(kk * 32 + ln) * T + tc] = fminf(thr, __fdiv_rn(neg_log_u32(us[kk]), beta));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.bnd_full[buf]);
+            }
+        }
+    }
+}
+
+// ---- scanner: the coupling blocks of a sub-window, fetched one sub-window ahead -------------------------
+// rows 0..31 of the buffer: J[32 sp + j][32 sc + .] (the previous sub-window's rows), rows 32..63: the diagonal block
+__device__ __forceinline__ void scan_prefetch(float *D, const float *__restrict__ Jn, int ldj, int n, int sp, int sc, int lane, bool vec16)
+{
+    if (vec16) {
+        const int chunk = lane & 7, rsub = lane >> 3;
+        const int col = sc * 32 + chunk * 4;
+#pragma unroll 4
+        for (int it = 0; it < 16; ++it) {
+            const int j = it * 4 + rsub;
+            const int row = (j < 32 ? sp * 32 + j : sc * 32 + j - 32);
+            const int bytes = (row < n) ? max(0, min(16, (n - col) * 4)) : 0;
+            cp_async16(D + j * 32 + chunk * 4, bytes > 0 ? (Jn + (size_t)row * (size_t)ldj + col) : Jn, bytes);
+        }
+    } else {
+        const int col = sc * 32 + lane;
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) {
+            const int row = (j < 32 ? sp * 32 + j : sc * 32 + j - 32);
+            const bool ok = (row < n) && (col < n);
+            cp_async4(D + j * 32 + lane, ok ? (Jn + (size_t)row * (size_t)ldj + col) : Jn, ok);
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams &p, const float *__restrict__ Jn, const float *__restrict__ betas,
+                             int W, int nlive, int lane)
+{
+    const int n = p.n;
+    const int S = (n + 31) >> 5;
+    const int tc = lane & 15, hf = lane >> 4;
+    const bool alive = tc < nlive, h0 = hf == 0;
+    const bool vec16 = ((p.ldj & 3) == 0) && ((reinterpret_cast<uintptr_t>(Jn) & 15u) == 0);
+    uint32_t r = 0;                                   // record counter
+    // what the previous record did to this lane's chain: rows, signs and magnitude of its coefficients
+    uint32_t prev_mask = 0u, prev_neg = 0u, prev_union = 0u;
+    float prev_mag = 1.0f;
+
+    // ---- records 0..S-1: the initial fields, F_i = h_i + sum_j J[j][i] s_j as dense updates with c = s_j ----
+    for (int s = 0; s < S; ++s, ++r) {
+        const uint32_t rb = r & (NREC - 1);
+        mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
+        const int rem = n - s * 32;
+        const uint32_t live = rem >= 32 ? FULL : ((1u << rem) - 1u);
+        float2 *crow = reinterpret_cast<float2 *>(sm.Cbuf) + (size_t)(rb * 32 + lane) * T;     // lane = row a of the panel
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const float c = ((sm.spinw[s * T + t] >> lane) & 1u) ? 1.0f : -1.0f;
+            crow[t] = make_float2(c, c);
+        }
+        if (lane == 0) {
+            sm.rec_meta[rb * 4 + 0] = live;
+            sm.rec_meta[rb * 4 + 1] = 0xffffffffu;                       // dense
+            sm.rec_meta[rb * 4 + 2] = (uint32_t)(s * 32);
+            sm.rec_meta[rb * 4 + 3] = 0u;
+        }
+        prev_union = live; prev_mask = live; prev_neg = ~sm.spinw[s * T + tc]; prev_mag = 1.0f;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.rec_full[rb]);
+    }
+
+    // ---- annealing ----
+    unsigned long long nacc = 0ull;
+    uint32_t t_sweep = 0, e = 0, wi = 0;
+    const unsigned long long hot_min =
+        p.hot_fraction > 0.0f ? (unsigned long long)((double)p.hot_fraction * (double)n * (double)nlive) : 0ull;
+    bool handed_over = false;
+    if (p.num_betas > 0) scan_prefetch(sm.Dbuf, Jn, p.ldj, n, S - 1, 0, lane, vec16);
+    for (int b = 0; b < p.num_betas && !handed_over; ++b) {
+        const float beta = __ldg(betas + b);
+        const float thr = __fdiv_rn(44.36142f, beta);
+        for (int sw = 0; sw < p.sweeps_per_beta && !handed_over; ++sw, ++t_sweep) {
+            const unsigned long long nacc_before = nacc;
+            for (int s = 0; s < S; ++s, ++r, ++e) {
+                const int k = s & 3;
+                const uint32_t rb = r & (NREC - 1), eb = e & 1u;
+                const float *D = sm.Dbuf + eb * (64 * 32);
+                // blocks of this sub-window have landed; fetch the next one's (the last prefetch of a launch is unused)
+                cp_async_wait_all();
+                __syncwarp();
+                scan_prefetch(sm.Dbuf + (eb ^ 1u) * (64 * 32), Jn, p.ldj, n, s, (s + 1 == S) ? 0 : s + 1, lane, vec16);
+                // exported fields: every flip up to record r-2 applied
+                float G[16];
+                mbar_wait(&sm.fx_full[eb], (e >> 1) & 1u);
+                {
+                    const float *fx = sm.Fx + eb * FXLD + hf * (16 * T + 16) + tc;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) G[i] = fx[i * T];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.fx_empty[eb]);
+                // record r-1 applied here, ahead of the appliers: same rows, same order, same coefficients
+                {
+                    const uint32_t off_s = smem_u32(D) + (uint32_t)hf * 64u;
+#pragma unroll 4
+                    for (int a = 0; a < 32; ++a) {
+                        if (!((prev_union >> a) & 1u)) continue;                              // warp-uniform
+                        const float c = ((prev_mask >> a) & 1u) ? (((prev_neg >> a) & 1u) ? -prev_mag : prev_mag) : 0.0f;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            const float4 d = lds128(off_s + (uint32_t)(a * 32 + q4 * 4) * 4u);
+                            G[4 * q4 + 0] = __fmaf_rn(c, d.x, G[4 * q4 + 0]);
+                            G[4 * q4 + 1] = __fmaf_rn(c, d.y, G[4 * q4 + 1]);
+                            G[4 * q4 + 2] = __fmaf_rn(c, d.z, G[4 * q4 + 2]);
+                            G[4 * q4 + 3] = __fmaf_rn(c, d.w, G[4 * q4 + 3]);
+                        }
+                    }
+                }
+                const uint32_t old = sm.spinw[s * T + tc];
+                const int rem = n - s * 32;
+                // ---- pre-check: can any chain accept anything here (dE < 44.36142/beta)? ----
+                bool cand = false;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int a = hf * 16 + i;
+                    const float dE = __fmul_rn(G[i], ((old >> a) & 1u) ? -2.0f : 2.0f);
+                    cand |= (a < rem) && (dE < thr);
+                }
+                cand = __any_sync(FULL, cand && alive);
+                if (k == 0) mbar_wait(&sm.bnd_full[wi & 1u], (wi >> 1) & 1u);
+                mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
+                uint32_t flipm = 0u;
+                if (cand) {
+                    // ---- scan (lane = chain tc + 16 * half; 16 variables of the sub-window per lane) ----
+                    // this lane's bound of variable a (its own half only): a load per step, independent of the decisions
+                    const float *bo = sm.bounds + (wi & 1u) * (4 * 32 * T) + (k * 32 + hf * 16) * T + tc;
+                    const uint32_t dbuf_s = smem_u32(D) + (uint32_t)(32 * 32) * 4u + (uint32_t)hf * 64u;
+                    const uint32_t cbuf_s = smem_u32(sm.Cbuf) + (uint32_t)(rb * 32 * T + tc) * 8u;
+                    // branch-free: every step applies c * D[a][.] with c = 0 for chains that keep variable a; the
+                    // shared-memory reads do not depend on the decisions (row a+1 is fetched before the vote of row a),
+                    // only field -> dE -> compare -> ballot -> c -> fma is a dependent chain
+                    float4 dcur[4], dnxt[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = lds128(dbuf_s + (uint32_t)(q4 * 4) * 4u);
+#pragma unroll
+                    for (int a = 0; a < 32; ++a) {
+                        const int ha = a >> 4, i = a & 15;
+                        if (a < 31) {
+#pragma unroll
+                            for (int q4 = 0; q4 < 4; ++q4) dnxt[q4] = lds128(dbuf_s + (uint32_t)((a + 1) * 32 + q4 * 4) * 4u);
+                        }
+                        const float sg = ((old >> a) & 1u) ? -2.0f : 2.0f;        // variable a has not been visited yet
+                        const float dE = __fmul_rn(G[i], sg);
+                        const bool acc = ((ha == 0) == h0) & alive & (a < rem) & ((dE <= 0.0f) | (dE < bo[i * T]));
+                        const uint32_t bal = __ballot_sync(FULL, acc);
+                        const uint32_t oldbal = __ballot_sync(FULL, (old >> a) & 1u);          // off the dependent chain
+                        if (lane == 0) sm.rowmask[rb * 32 + a] = ((bal >> (16 * ha)) & 0xffffu) | (oldbal << 16);
+                        const bool mine = (bal >> (16 * ha + tc)) & 1u;
+                        const float c = mine ? sg : 0.0f;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) {
+                            G[4 * q4 + 0] = __fmaf_rn(c, dcur[q4].x, G[4 * q4 + 0]);
+                            G[4 * q4 + 1] = __fmaf_rn(c, dcur[q4].y, G[4 * q4 + 1]);
+                            G[4 * q4 + 2] = __fmaf_rn(c, dcur[q4].z, G[4 * q4 + 2]);
+                            G[4 * q4 + 3] = __fmaf_rn(c, dcur[q4].w, G[4 * q4 + 3]);
+                        }
+                        if (h0) asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(cbuf_s + (uint32_t)a * (T * 8u)), "f"(c) : "memory");
+                        flipm |= (mine ? 1u : 0u) << a;
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = dnxt[q4];
+                    }
+                }
+                const uint32_t unionm = __reduce_or_sync(FULL, flipm);
+                const uint32_t cnt = __reduce_add_sync(FULL, h0 ? (uint32_t)__popc(flipm) : 0u);
+                if (h0) sm.spinw[s * T + tc] = old ^ flipm;
+                if (lane == 0) {
+                    sm.rec_meta[rb * 4 + 0] = unionm;
+                    sm.rec_meta[rb * 4 + 1] = cnt;
+                    sm.rec_meta[rb * 4 + 2] = (uint32_t)(s * 32);
+                    sm.rec_meta[rb * 4 + 3] = 0u;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&sm.rec_full[rb]);
+                    if (k == 3 || s + 1 == S) mbar_arrive(&sm.bnd_empty[wi & 1u]);      // bounds of this window consumed
+                }
+                if (k == 3 || s + 1 == S) ++wi;
+                nacc += cnt;
+                prev_union = unionm; prev_mask = flipm; prev_neg = old; prev_mag = 2.0f;
+            }
+            // two-phase schedule: once a sweep accepts less than hot_fraction of its proposals the chains are cheaper to
+            // advance one warp each (rows no longer shared by most chains)
+            if (hot_min > 0ull && nacc - nacc_before < hot_min) handed_over = true;
+        }
+    }
+    cp_async_wait_all();
+    // ---- exit record; release the bounds warp ----
+    {
+        const uint32_t rb = r & (NREC - 1);
+        mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
+        if (lane == 0) {
+            sm.rec_meta[rb * 4 + 0] = 0u;
+            sm.rec_meta[rb * 4 + 1] = 0u;
+            sm.rec_meta[rb * 4 + 2] = 0u;
+            sm.rec_meta[rb * 4 + 3] = 1u;
+            *reinterpret_cast<volatile uint32_t *>(sm.ctl) = 1u;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sm.rec_full[rb]);
+            mbar_arrive(&sm.bnd_empty[0]);
+            mbar_arrive(&sm.bnd_empty[1]);
+        }
+    }
+    if (lane == 0) {
+        if (p.sweeps_done != nullptr) p.sweeps_done[blockIdx.x] = t_sweep;      // completed sweeps of this tile
+        if (p.counters != nullptr) {
+            atomicAdd(p.counters + 0, nacc);
+            atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)t_sweep * (unsigned long long)nlive);
+        }
+    }
+    tile_sync((W + 1) * 32);          // spins final: the appliers write the states
+}
+
+// NS == 8 (n > 1024): W = windows / 2 applier warps x 8 columns; NS == 4 (n <= 1024): W = windows applier warps x 4 columns.
+template <int NS>
 __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, const int W, const int ctas_per_problem)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -337,46 +572,51 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     const int warp = threadIdx.x >> 5;
     const int n = p.n, ld = p.ld;
     const int S = (n + 31) >> 5;                       // populated 32-variable sub-windows
-    const TileSmem sm = carve(smem_raw, ld);
-    const int ncons = W * 32;
+    const TileSmem sm = carve(smem_raw);
 
     const long long q = blockIdx.x / ctas_per_problem;
     const long long r0 = (long long)(blockIdx.x % ctas_per_problem) * T;
     const int nlive = (int)min((long long)T, p.num_reads - r0);
     const float *__restrict__ Jp = p.Jp + (size_t)q * (size_t)n * (size_t)ld;
+    const float *__restrict__ betas = p.beta + q * p.beta_stride;
+    const long long cl0 = q * p.num_reads + r0;        // row of chain 0 of this CTA in init / out
+    const unsigned long long chain0 = p.chain_offset + (unsigned long long)((p.flags & 2u) ? r0 : cl0);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NGS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], (uint32_t)W); }
-        mbar_init(&sm.work_full[0], 1);
-        mbar_init(&sm.work_full[1], 1);
+        for (int i = 0; i < NREC; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], (uint32_t)W + 1u); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&sm.fx_full[i], 1); mbar_init(&sm.fx_empty[i], 1);
+            mbar_init(&sm.bnd_full[i], 1); mbar_init(&sm.bnd_empty[i], 1);
+        }
+        sm.ctl[0] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    if (NS == 8) {
-        if (warp >= 8) {
-            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-            if (warp == 8 && lane == 0) tile_producer(sm, Jp, ld);
-            return;
+    if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_HELPER));
+        if (warp == WARP_PRODUCER) {
+            if (lane == 0) tile_producer(sm, Jp, ld);
+        } else if (warp == WARP_BOUNDS) {
+            tile_bounds(sm, p, betas, chain0, lane);
+        } else if (warp == WARP_SCANNER) {
+            tile_sync((W + 1) * 32);                    // initial spins written
+            tile_scanner(sm, p, p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj, betas, W, nlive, lane);
         }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-        if (warp >= W) return;                          // idle consumer-warpgroup warps (W < 8)
-    } else if (warp == W) {
-        if (lane == 0) tile_producer(sm, Jp, ld);
         return;
     }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_APPLIER));
+    if (warp >= W) return;                              // idle warps of the applier warpgroups (W < 8)
 
-    // ================================= consumer warps =================================
+    // ================================= applier warps =================================
     constexpr int NWIN = NS / 4;
     const float *__restrict__ hq = p.hp + (size_t)q * (size_t)ld;
-    const float *__restrict__ Jn = p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj;
-    const float *__restrict__ betas = p.beta + q * p.beta_stride;
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-    const long long cl0 = q * p.num_reads + r0;        // row of chain 0 of this CTA in init / out
-    const unsigned long long chain0 = p.chain_offset + (unsigned long long)((p.flags & 2u) ? r0 : cl0);
     const uint32_t dense_pct = ((p.flags >> 8) & 0xffu) ? ((p.flags >> 8) & 0xffu) : 40u;
     const uint32_t dense_min = max(1u, (uint32_t)nlive * 32u * dense_pct / 100u);
     const int tid = threadIdx.x;
+    const int ncons = W * 32;
 
     // ---- initial spins ----
     if (p.init != nullptr) {
@@ -399,7 +639,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             sm.spinw[s * T + t] = (t < nlive) ? wd : 0u;
         }
     }
-    // ---- fields: F_i = h_i, then F_i = fma(J[j][i], s_j, F_i) for j = 0..n-1 (dense updates with c = s_j) ----
+    tile_sync((W + 1) * 32);                            // the scanner takes the spins from here on
+
     float2 F2[NS / 2][T];      // F2[jw*2 + h][t] = fields of sub-windows (2h, 2h+1) of window jw, chain t
 #pragma unroll
     for (int jw = 0; jw < NWIN; ++jw) {
@@ -414,192 +655,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     A.cbuf = smem_u32(sm.Cbuf);
     A.full = smem_u32(sm.full);
     A.empty = smem_u32(sm.empty);
-    A.flip = smem_u32(sm.rec_flip);
-    A.old = smem_u32(sm.rec_old);
-    uint32_t kq = 0, ri = 0;
-    consumer_sync(ncons);
-    for (int s = 0; s < S; ++s) {
-        const int par = s & 1;
-        if (warp == 0) {
-            const int rem = n - s * 32;
-            const uint32_t live = rem >= 32 ? FULL : ((1u << rem) - 1u);
-            // lane = row a of the panel: coefficients s_a(t) = +-1 for all chains
-            float *crow = sm.Cbuf + (size_t)(par * 32 + lane) * T;
-#pragma unroll
-            for (int t = 0; t < T; ++t) crow[t] = ((sm.spinw[s * T + t] >> lane) & 1u) ? 1.0f : -1.0f;
-            if (lane == 0) {
-                sm.rec_meta[par * 4 + 0] = live;
-                sm.rec_meta[par * 4 + 1] = 0xffffffffu;          // dense
-                sm.work[(kq & 1u) * 4 + 0] = live;
-                sm.work[(kq & 1u) * 4 + 1] = (uint32_t)(s * 32);
-                sm.work[(kq & 1u) * 4 + 2] = 0u;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.work_full[kq & 1u]);
-        }
-        ++kq;
-        consumer_sync(ncons);
-        apply_record<NS>(F2, A, sm.rec_meta[par * 4 + 0], 0xffffffffu, par, lane, ri, 0u);
-    }
-    consumer_sync(ncons);
+    A.rowmask = smem_u32(sm.rowmask);
 
-    // ---- annealing ----
-    unsigned long long nacc = 0ull;
-    uint32_t t_sweep = 0;
-    bool handed_over = false;
-    const unsigned long long hot_min =
-        p.hot_fraction > 0.0f ? (unsigned long long)((double)p.hot_fraction * (double)n * (double)nlive) : 0ull;
-    uint32_t pi = 0;                                   // running sub-window counter: parity of the record buffers
-    for (int b = 0; b < p.num_betas && !handed_over; ++b) {
-        const float beta = __ldg(betas + b);
-        const float thr = __fdiv_rn(44.36142f, beta);
-        for (int sw = 0; sw < p.sweeps_per_beta && !handed_over; ++sw, ++t_sweep) {
-            const unsigned long long nacc_before = nacc;
-            int bounds_window = -1;
-            for (int s = 0; s < S; ++s, ++pi) {
-                const int g = s >> 2, k = s & 3;
-                const int owner = g % W, jw_own = g / W;
-                const int par = (int)(pi & 1u);
-                const bool is_owner = (warp == owner);
-                float Fs[T];
-                if (is_owner) {
-                    // ---- pre-check (lane = variable 32 s + lane) ----
-                    const int slot = jw_own * 4 + k;
+    // ---- records: S initial-field records, then one per sub-window and sweep, until the exit record ----
+    uint32_t gi = 0;
+    int s_next = 0;                                     // sub-window of record r + 1 once annealing has started
+    for (uint32_t r = 0;; ++r) {
+        if (r + 1 >= (uint32_t)S) {
+            // record r + 1 belongs to sub-window s_next: its owner hands the scanner that sub-window's fields (all
+            // records before r applied), from which the scanner decides record r + 1 while record r is applied here
+            const uint32_t e1 = r + 1 - (uint32_t)S;
+            const int g1 = s_next >> 2, k1s = s_next & 3;
+            if (g1 % W == warp) {
+                const int slot = (g1 / W) * 4 + k1s;
+                mbar_wait(&sm.fx_empty[e1 & 1u], ((e1 >> 1) & 1u) ^ 1u);
+                float4 *dst = reinterpret_cast<float4 *>(sm.Fx + (e1 & 1u) * FXLD + lane * T + (lane >> 4) * 16);
+                // register arrays need static indices: one copy of the four stores per column slot, the slot is warp-uniform
 #pragma unroll
-                    for (int j = 0; j < NS; ++j)
-                        if (j == slot) {
+                for (int j = 0; j < NS; ++j)
+                    if (j == slot) {
 #pragma unroll
-                            for (int t = 0; t < T; ++t) Fs[t] = (j & 1) ? F2[j >> 1][t].y : F2[j >> 1][t].x;
-                        }
-                    const bool vlive = (s * 32 + lane) < n;
-                    bool cand = false;
-#pragma unroll
-                    for (int q4 = 0; q4 < T / 4; ++q4) {
-                        const uint4 w4 = reinterpret_cast<const uint4 *>(sm.spinw + s * T)[q4];
-                        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int t = q4 * 4 + e;
-                            const float dE = __fmul_rn(Fs[t], ((ws[e] >> lane) & 1u) ? -2.0f : 2.0f);
-                            cand |= (t < nlive) && (dE < thr);
-                        }
+                        for (int q4 = 0; q4 < T / 4; ++q4)
+                            dst[q4] = (j & 1) ? make_float4(F2[j >> 1][4 * q4].y, F2[j >> 1][4 * q4 + 1].y, F2[j >> 1][4 * q4 + 2].y, F2[j >> 1][4 * q4 + 3].y)
+                                              : make_float4(F2[j >> 1][4 * q4].x, F2[j >> 1][4 * q4 + 1].x, F2[j >> 1][4 * q4 + 2].x, F2[j >> 1][4 * q4 + 3].x);
                     }
-                    cand = __any_sync(FULL, cand && vlive);
-                    if (lane == 0) sm.rec_meta[par * 4 + 2] = cand ? 1u : 0u;
-                    if (cand) {
-                        // diagonal block J[32s + a][32s + lane], natural order, for the scan
-                        const int col = s * 32 + lane;
-#pragma unroll 8
-                        for (int a = 0; a < 32; ++a) {
-                            const int row = s * 32 + a;
-                            const bool ok = (row < n) && (col < n);
-                            cp_async4(sm.Dbuf + a * 32 + lane, ok ? (Jn + (size_t)row * (size_t)p.ldj + col) : Jn, ok);
-                        }
-                    }
-                }
-                consumer_sync(ncons);                                                          // (A)
-                if (sm.rec_meta[par * 4 + 2] == 0u) continue;
-                if (bounds_window != g) {
-                    // ---- acceptance bounds of window g for all chains: min(thr, -ln(u/2^32)/beta) ----
-                    for (int task = tid; task < 32 * T; task += ncons) {
-                        const int tc = task % T, ln = task / T;
-                        const unsigned long long chain = chain0 + (unsigned long long)tc;
-                        const Philox4 o = philox4x32_10((uint32_t)chain, (uint32_t)(chain >> 32), t_sweep, (uint32_t)(g * 32 + ln), k0, k1);
-                        const uint32_t us[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            sm.bounds[(kk * 32 + ln) * T + tc] = fminf(thr, __fdiv_rn(neg_log_u32(us[kk]), beta));
-                    }
-                    bounds_window = g;
-                    consumer_sync(ncons);                                                      // (B)
-                }
-                if (is_owner) {
-                    // ---- scan (lane = chain tc + 16 * half; 16 variables of the sub-window per lane) ----
-                    const int tc = lane & 15, hf = lane >> 4;
-#pragma unroll
-                    for (int t = 0; t < T; ++t) sm.Xbuf[t * XLD + lane] = Fs[t];
-                    __syncwarp();
-                    float G[16], bnd[16];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const float4 x4 = reinterpret_cast<const float4 *>(sm.Xbuf + tc * XLD + hf * 16)[q4];
-                        G[4 * q4] = x4.x; G[4 * q4 + 1] = x4.y; G[4 * q4 + 2] = x4.z; G[4 * q4 + 3] = x4.w;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) bnd[i] = sm.bounds[(k * 32 + hf * 16 + i) * T + tc];
-                    const uint32_t old = sm.spinw[s * T + tc];
-                    const uint32_t dbuf_s = smem_u32(sm.Dbuf) + (uint32_t)hf * 64u;
-                    const uint32_t cbuf_s = smem_u32(sm.Cbuf) + (uint32_t)(par * 32 * T + tc) * 4u;
-                    const bool alive = tc < nlive;
-                    const int rem = n - s * 32;
-                    uint32_t flipm = 0u;
-                    cp_async_wait_all();
-                    __syncwarp();
-                    // branch-free: every step applies c * D[a][.] with c = 0 for chains that keep variable a; the
-                    // shared-memory reads do not depend on the decisions (row a+1 is fetched before the vote of row a),
-                    // only field -> dE -> compare -> ballot -> c -> fma is a dependent chain
-                    const bool h0 = hf == 0;
-                    float4 dcur[4], dnxt[4];
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = lds128(dbuf_s + (uint32_t)(q4 * 4) * 4u);
-#pragma unroll
-                    for (int a = 0; a < 32; ++a) {
-                        const int ha = a >> 4, i = a & 15;
-                        if (a < 31) {
-#pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) dnxt[q4] = lds128(dbuf_s + (uint32_t)((a + 1) * 32 + q4 * 4) * 4u);
-                        }
-                        const float sg = ((old >> a) & 1u) ? -2.0f : 2.0f;        // variable a has not been visited yet
-                        const float dE = __fmul_rn(G[i], sg);
-                        const bool acc = ((ha == 0) == h0) & alive & (a < rem) & ((dE <= 0.0f) | (dE < bnd[i]));
-                        const uint32_t bal = __ballot_sync(FULL, acc);
-                        const bool mine = (bal >> (16 * ha + tc)) & 1u;
-                        const float c = mine ? sg : 0.0f;
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
-                            G[4 * q4 + 0] = __fmaf_rn(c, dcur[q4].x, G[4 * q4 + 0]);
-                            G[4 * q4 + 1] = __fmaf_rn(c, dcur[q4].y, G[4 * q4 + 1]);
-                            G[4 * q4 + 2] = __fmaf_rn(c, dcur[q4].z, G[4 * q4 + 2]);
-                            G[4 * q4 + 3] = __fmaf_rn(c, dcur[q4].w, G[4 * q4 + 3]);
-                        }
-                        if (h0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbuf_s + (uint32_t)a * (T * 4u)), "f"(c) : "memory");
-                        flipm |= (mine ? 1u : 0u) << a;
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = dnxt[q4];
-                    }
-                    const uint32_t spin = old ^ flipm;
-                    const uint32_t unionm = __reduce_or_sync(FULL, flipm);
-                    const uint32_t cnt = __reduce_add_sync(FULL, hf == 0 ? (uint32_t)__popc(flipm) : 0u);
-                    if (hf == 0) {
-                        sm.spinw[s * T + tc] = spin;
-                        sm.rec_flip[par * T + tc] = flipm;
-                        sm.rec_old[par * T + tc] = old;
-                    }
-                    if (lane == 0) {
-                        sm.rec_meta[par * 4 + 0] = unionm;
-                        sm.rec_meta[par * 4 + 1] = cnt;
-                        if (unionm) {
-                            sm.work[(kq & 1u) * 4 + 0] = unionm;
-                            sm.work[(kq & 1u) * 4 + 1] = (uint32_t)(s * 32);
-                            sm.work[(kq & 1u) * 4 + 2] = 0u;
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0 && unionm) mbar_arrive(&sm.work_full[kq & 1u]);
-                }
-                consumer_sync(ncons);                                                          // (C)
-                if (sm.rec_meta[par * 4 + 0] != 0u) {
-                    nacc += sm.rec_meta[par * 4 + 1];
-                    ++kq;
-                    apply_record<NS>(F2, A, sm.rec_meta[par * 4 + 0], sm.rec_meta[par * 4 + 1], par, lane, ri, dense_min);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.fx_full[e1 & 1u]);
             }
-            // two-phase schedule: once a sweep accepts less than hot_fraction of its proposals the chains are cheaper to
-            // advance one warp each (rows no longer shared by most chains); every consumer thread sees the same counts
-            if (hot_min > 0ull && nacc - nacc_before < hot_min) handed_over = true;
+            s_next = (s_next + 1 == S) ? 0 : s_next + 1;
         }
+        const uint32_t rb = r & (NREC - 1);
+        mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u);
+        const uint32_t u = sm.rec_meta[rb * 4 + 0], cnt = sm.rec_meta[rb * 4 + 1], ex = sm.rec_meta[rb * 4 + 3];
+        if (ex) break;
+        if (u != 0u) apply_record<NS>(F2, A, u, cnt, rb, lane, gi, dense_min);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.rec_empty[rb]);
     }
-    consumer_sync(ncons);
+
     if (p.fields != nullptr) {
         // fields in the warp kernel's layout: chain-major, float4 (sub-windows 0..3) per lane and 128-variable window
 #pragma unroll
@@ -611,15 +704,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
                     *reinterpret_cast<float4 *>(p.fields + (size_t)(cl0 + t) * (size_t)ld + off) =
                         make_float4(F2[jw * 2][t].x, F2[jw * 2][t].y, F2[jw * 2 + 1][t].x, F2[jw * 2 + 1][t].y);
         }
-        if (tid == 0) p.sweeps_done[blockIdx.x] = t_sweep;            // completed sweeps of this tile
     }
 
-    // ---- write-back: states in natural variable order, 0/1; stop the producer ----
-    if (tid == 0) {
-        sm.work[(kq & 1u) * 4 + 0] = 0u;
-        sm.work[(kq & 1u) * 4 + 2] = 1u;
-        mbar_arrive(&sm.work_full[kq & 1u]);
-    }
+    // ---- write-back: states in natural variable order, 0/1 ----
+    tile_sync((W + 1) * 32);
     for (int t = warp; t < nlive; t += W) {
         int8_t *o = p.out + (size_t)(cl0 + t) * (size_t)n;
         for (int s = 0; s < S; ++s) {
@@ -627,16 +715,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             if (v < n) o[v] = (int8_t)((sm.spinw[s * T + t] >> lane) & 1u);
         }
     }
-    if (p.counters != nullptr && tid == 0) {
-        atomicAdd(p.counters + 0, nacc);
-        atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)t_sweep * (unsigned long long)nlive);
-    }
 }
 
-template <int NS, int NTHREADS>
+template <int NS>
 int launch_tile(const SaParams &p, int W, cudaStream_t st)
 {
-    auto kern = sa_tile_kernel<NS, NTHREADS>;
+    auto kern = sa_tile_kernel<NS>;
     const long long cpp = (p.num_reads + T - 1) / T;
     const long long blocks = cpp * p.batch_q;
     if (blocks > 0x7fffffffLL) {
@@ -644,13 +728,9 @@ int launch_tile(const SaParams &p, int W, cudaStream_t st)
         return QBM_EUNSUPPORTED;
     }
     const size_t smem = tile_smem_bytes(p.ld);
-    static size_t attr_set[2] = {0, 0};
-    size_t &cur = attr_set[NS == 8 ? 1 : 0];
-    if (smem > cur) {
-        QBM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cur = smem;
-    }
-    kern<<<(unsigned)blocks, NS == 8 ? NTHREADS : (W + 1) * 32, smem, st>>>(p, W, (int)cpp);
+    // per launch, not cached: the attribute belongs to the current device, and a process may drive several
+    QBM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, NTHREADS, smem, st>>>(p, W, (int)cpp);
     QBM_LAUNCH_OK("sa_tile_kernel");
     return QBM_OK;
 }
@@ -660,7 +740,7 @@ int launch_tile(const SaParams &p, int W, cudaStream_t st)
 bool sa_tile_supported(int n) { return n >= 1 && n <= QBM_SA_MAX_N; }
 
 // row length of the permuted coupling matrix the tile kernel reads: whole 128-variable windows, one
-// (n <= 1024) or two (n > 1024) per consumer warp
+// (n <= 1024) or two (n > 1024) per applier warp
 int sa_tile_ld(int n)
 {
     const int win = (n + 127) / 128;
@@ -671,6 +751,6 @@ int sa_tile_ld(int n)
 int sa_tile_launch(const SaParams &p, cudaStream_t st)
 {
     const int win = p.ld / 128;
-    if (win <= 8) return launch_tile<4, 9 * 32>(p, win, st);               // n <= 1024: W = win consumer warps x 4 columns
-    return launch_tile<8, 384>(p, win / 2, st);                            // n >  1024: W = win / 2 consumer warps x 8 columns
+    if (win <= 8) return launch_tile<4>(p, win, st);                       // n <= 1024: W = win applier warps x 4 columns
+    return launch_tile<8>(p, win / 2, st);                                 // n >  1024: W = win / 2 applier warps x 8 columns
 }
