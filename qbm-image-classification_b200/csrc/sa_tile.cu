@@ -71,6 +71,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// wait that gives up when `*flag` becomes non-zero (the bounds warp runs ahead of a scanner that may stop early);
+// try_wait suspends for a bounded time, so the flag is polled between attempts.  Returns false when it gave up.
+__device__ __forceinline__ bool mbar_wait_or_flag(uint64_t *bar, uint32_t parity, volatile uint32_t *flag)
+{
+    const uint32_t a = smem_u32(bar);
+    while (true) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+        if (*flag != 0u) return false;
+    }
+}
 __device__ __forceinline__ void mbar_arrive_s(uint32_t bar_s)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
@@ -88,11 +105,20 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
         "}" ::"r"(bar_s), "r"(parity) : "memory");
 }
 // two fp32 FMAs per instruction (Blackwell FFMA2): acc.{x,y} = fma(a.{x,y}, b.{x,y}, acc.{x,y}), each IEEE round-to-nearest
-__device__ __forceinline__ void ffma2(float2 &acc, const float2 a, const float2 b)
+// The accumulators are kept as packed 64-bit values for their whole life (fields of two adjacent sub-windows of a lane):
+// with float2 accumulators the pack / unpack around every FFMA2 of the row loop survives as register moves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
 {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;"
-        : "+l"(reinterpret_cast<unsigned long long &>(acc))
-        : "l"(reinterpret_cast<const unsigned long long &>(a)), "l"(reinterpret_cast<const unsigned long long &>(b)));
+    f32x2 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ float lo2(f32x2 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi2(f32x2 v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ void ffma2(f32x2 &acc, const f32x2 a, const f32x2 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
 {
@@ -216,73 +242,73 @@ __device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uin
 }
 
 template <int NS>
-__device__ __forceinline__ void row_apply_dense(float2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
+__device__ __forceinline__ void row_apply_dense(f32x2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
     // coefficients come as ready (c, c) pairs, two chains per 128-bit load (warp-uniform address: a broadcast)
 #pragma unroll
     for (int t2 = 0; t2 < T / 2; ++t2) {
         const float4 c4 = lds128(R.c + (uint32_t)t2 * 16u);
-        const float2 ca = make_float2(c4.x, c4.y), cb = make_float2(c4.z, c4.w);
+        const f32x2 ca = pack2(c4.x, c4.y), cb = pack2(c4.z, c4.w);
 #pragma unroll
         for (int jw = 0; jw < NS / 4; ++jw) {
-            ffma2(F2[jw * 2 + 0][2 * t2], ca, make_float2(R.r[jw].x, R.r[jw].y));
-            ffma2(F2[jw * 2 + 1][2 * t2], ca, make_float2(R.r[jw].z, R.r[jw].w));
-            ffma2(F2[jw * 2 + 0][2 * t2 + 1], cb, make_float2(R.r[jw].x, R.r[jw].y));
-            ffma2(F2[jw * 2 + 1][2 * t2 + 1], cb, make_float2(R.r[jw].z, R.r[jw].w));
+            const f32x2 r01 = pack2(R.r[jw].x, R.r[jw].y), r23 = pack2(R.r[jw].z, R.r[jw].w);
+            ffma2(F2[jw * 2 + 0][2 * t2], ca, r01);
+            ffma2(F2[jw * 2 + 1][2 * t2], ca, r23);
+            ffma2(F2[jw * 2 + 0][2 * t2 + 1], cb, r01);
+            ffma2(F2[jw * 2 + 1][2 * t2 + 1], cb, r23);
         }
     }
 }
 
 template <int NS>
-__device__ __forceinline__ void row_apply_sparse(float2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
+__device__ __forceinline__ void row_apply_sparse(f32x2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
     const uint32_t m = R.c;              // bits 0..15: chains that flipped this variable, bits 16..31: their old spins
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         if ((m >> t) & 1u) {             // warp-uniform
             const float c = ((m >> (16 + t)) & 1u) ? -2.0f : 2.0f;
-            const float2 cc = make_float2(c, c);
+            const f32x2 cc = pack2(c, c);
 #pragma unroll
             for (int jw = 0; jw < NS / 4; ++jw) {
-                ffma2(F2[jw * 2 + 0][t], cc, make_float2(R.r[jw].x, R.r[jw].y));
-                ffma2(F2[jw * 2 + 1][t], cc, make_float2(R.r[jw].z, R.r[jw].w));
+                ffma2(F2[jw * 2 + 0][t], cc, pack2(R.r[jw].x, R.r[jw].y));
+                ffma2(F2[jw * 2 + 1][t], cc, pack2(R.r[jw].z, R.r[jw].w));
             }
         }
     }
 }
 
 template <int NS>
-__device__ __forceinline__ void apply_record(float2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, uint32_t rb,
+__device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, uint32_t rb,
                                              int lane, uint32_t &gi, uint32_t dense_min)
 {
     const uint32_t cb_rec = A.cbuf + rb * (32u * T * 8u);
     const uint32_t rm_rec = A.rowmask + rb * (32u * 4u);
-    RowRegs<NS> Ra, Rb;
-    uint32_t sa, sb, k = 0;
-    // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2};
-    // sparse: per chain a warp-uniform test of the row's mask word.
-    // Two register buffers: the loads of the next row are in flight while the FMAs of this row issue
-    const bool dense = count >= dense_min;
-    row_fetch<NS>(Ra, A, u, gi, k, cb_rec, rm_rec, sa, dense);
-    while (true) {
-        const bool more_b = u != 0u;
-        if (more_b) row_fetch<NS>(Rb, A, u, gi, k, cb_rec, rm_rec, sb, dense);
-        if (dense) row_apply_dense<NS>(F2, Ra);
-        else row_apply_sparse<NS>(F2, Ra);
-        if (sa != NONE) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sa * 8u);
+    RowRegs<NS> R;
+    uint32_t rel, k = 0;
+    // one row at a time (the other applier warp of the scheduler covers the load latency; a second register buffer costs
+    // more in spilled fields than it hides).  The dense and the sparse loop are kept apart: one loop with both bodies
+    // makes ptxas reconcile the 128 field registers with moves
+    if (count >= dense_min) {
+        // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2}
+        while (u != 0u) {
+            row_fetch<NS>(R, A, u, gi, k, cb_rec, rm_rec, rel, true);
+            row_apply_dense<NS>(F2, R);
+            if (rel != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + rel * 8u);
+            }
         }
-        if (!more_b) break;
-        const bool more_a = u != 0u;
-        if (more_a) row_fetch<NS>(Ra, A, u, gi, k, cb_rec, rm_rec, sa, dense);
-        if (dense) row_apply_dense<NS>(F2, Rb);
-        else row_apply_sparse<NS>(F2, Rb);
-        if (sb != NONE) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive_s(A.empty + sb * 8u);
+    } else {
+        // sparse: per chain a warp-uniform test of the row's mask word
+        while (u != 0u) {
+            row_fetch<NS>(R, A, u, gi, k, cb_rec, rm_rec, rel, false);
+            row_apply_sparse<NS>(F2, R);
+            if (rel != NONE) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive_s(A.empty + rel * 8u);
+            }
         }
-        if (!more_a) break;
     }
 }
 
@@ -329,8 +355,7 @@ __device__ __forceinline__ void tile_bounds(const TileSmem &sm, const SaParams &
         for (int sw = 0; sw < p.sweeps_per_beta; ++sw, ++t_sweep) {
             for (int g = 0; g < nwin; ++g, ++wi) {
                 const uint32_t buf = wi & 1u;
-                mbar_wait(&sm.bnd_empty[buf], ((wi >> 1) & 1u) ^ 1u);
-                if (ctl[0] != 0u) return;
+                if (!mbar_wait_or_flag(&sm.bnd_empty[buf], ((wi >> 1) & 1u) ^ 1u, ctl)) return;    // the scanner has stopped
                 float *bo = sm.bounds + buf * (4 * 32 * T);
 #pragma unroll 2
                 for (int task = lane; task < 32 * T; task += 32) {
@@ -535,7 +560,7 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
         }
     }
     cp_async_wait_all();
-    // ---- exit record; release the bounds warp ----
+    // ---- exit record; the flag stops the bounds warp, which polls it while it waits for a free buffer ----
     {
         const uint32_t rb = r & (NREC - 1);
         mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
@@ -547,11 +572,7 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
             *reinterpret_cast<volatile uint32_t *>(sm.ctl) = 1u;
         }
         __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&sm.rec_full[rb]);
-            mbar_arrive(&sm.bnd_empty[0]);
-            mbar_arrive(&sm.bnd_empty[1]);
-        }
+        if (lane == 0) mbar_arrive(&sm.rec_full[rb]);
     }
     if (lane == 0) {
         if (p.sweeps_done != nullptr) p.sweeps_done[blockIdx.x] = t_sweep;      // completed sweeps of this tile
@@ -641,12 +662,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     }
     tile_sync((W + 1) * 32);                            // the scanner takes the spins from here on
 
-    float2 F2[NS / 2][T];      // F2[jw*2 + h][t] = fields of sub-windows (2h, 2h+1) of window jw, chain t
+    f32x2 F2[NS / 2][T];       // F2[jw*2 + h][t] = packed fields of sub-windows (2h, 2h+1) of window jw, chain t
 #pragma unroll
     for (int jw = 0; jw < NWIN; ++jw) {
         const float4 hv = __ldg(reinterpret_cast<const float4 *>(hq + (size_t)(jw * W + warp) * 128 + lane * 4));
 #pragma unroll
-        for (int t = 0; t < T; ++t) { F2[jw * 2 + 0][t] = make_float2(hv.x, hv.y); F2[jw * 2 + 1][t] = make_float2(hv.z, hv.w); }
+        for (int t = 0; t < T; ++t) { F2[jw * 2 + 0][t] = pack2(hv.x, hv.y); F2[jw * 2 + 1][t] = pack2(hv.z, hv.w); }
     }
     TileAddr A;
     A.ring = smem_u32(sm.ring) + (uint32_t)(warp * 32 + lane) * 16u;
@@ -676,8 +697,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
                     if (j == slot) {
 #pragma unroll
                         for (int q4 = 0; q4 < T / 4; ++q4)
-                            dst[q4] = (j & 1) ? make_float4(F2[j >> 1][4 * q4].y, F2[j >> 1][4 * q4 + 1].y, F2[j >> 1][4 * q4 + 2].y, F2[j >> 1][4 * q4 + 3].y)
-                                              : make_float4(F2[j >> 1][4 * q4].x, F2[j >> 1][4 * q4 + 1].x, F2[j >> 1][4 * q4 + 2].x, F2[j >> 1][4 * q4 + 3].x);
+                            dst[q4] = (j & 1) ? make_float4(hi2(F2[j >> 1][4 * q4]), hi2(F2[j >> 1][4 * q4 + 1]), hi2(F2[j >> 1][4 * q4 + 2]), hi2(F2[j >> 1][4 * q4 + 3]))
+                                              : make_float4(lo2(F2[j >> 1][4 * q4]), lo2(F2[j >> 1][4 * q4 + 1]), lo2(F2[j >> 1][4 * q4 + 2]), lo2(F2[j >> 1][4 * q4 + 3]));
                     }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.fx_full[e1 & 1u]);
@@ -702,7 +723,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             for (int t = 0; t < T; ++t)
                 if (t < nlive)
                     *reinterpret_cast<float4 *>(p.fields + (size_t)(cl0 + t) * (size_t)ld + off) =
-                        make_float4(F2[jw * 2][t].x, F2[jw * 2][t].y, F2[jw * 2 + 1][t].x, F2[jw * 2 + 1][t].y);
+                        make_float4(lo2(F2[jw * 2][t]), hi2(F2[jw * 2][t]), lo2(F2[jw * 2 + 1][t]), hi2(F2[jw * 2 + 1][t]));
         }
     }
 
