@@ -255,7 +255,9 @@ int qbm_rbm_workspace_layout(int B, int V, int H, int C, long long *offsets);
  * Measurement hook (no reference counterpart): on-chip peaks of the current device, the denominators of the
  * sampler's rooflines.  Streams FFMA2 / FFMA, conflict-free LDS.128 and L1-hit LDG.128 loops for a
  * few milliseconds each, timed with CUDA events; SYNCHRONISES `stream`.
- *   out     host double[4]: fp32 TFLOP/s with fma.rn.f32x2, fp32 TFLOP/s with fma.rn.f32, shared-memory TB/s, L1 TB/s
+ *   out     host double[6]: fp32 TFLOP/s with fma.rn.f32x2, fp32 TFLOP/s with fma.rn.f32, shared-memory TB/s, L1 TB/s,
+ *           fp32 TFLOP/s of fma.rn.f32x2 with three distinct register operands at 8 warps per SM (the chain-tile kernel's
+ *           row update), coefficient-major and row-major instruction order
  *   scratch device buffer, 16-byte aligned, at least 1 MiB + 16 bytes
  */
 int qbm_probe_onchip_peaks(double *out, void *scratch, size_t scratch_bytes, void *stream);

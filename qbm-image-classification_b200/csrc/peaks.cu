@@ -39,6 +39,40 @@ __global__ void __launch_bounds__(PK_THREADS) peak_fma_kernel(float *out, int it
     if (s == 123.456f) out[0] = s;                      // never true: keeps the accumulators alive
 }
 
+// FFMA2 with the operand pattern of the chain-tile kernel's row update (sa_tile.cu): 64 packed accumulators,
+// acc[4 t + j] = fma(c[t], r[j], acc[4 t + j]) -- three distinct 64-bit register operands per instruction.
+// ORDER 0: coefficient-major (4 consecutive instructions share c[t]); ORDER 1: row-major (16 consecutive share r[j])
+template <int ORDER>
+__global__ void __launch_bounds__(256) peak_fma_tile_kernel(float *out, int iters, float a, float b)
+{
+    unsigned long long acc[64], c[16], r[4];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = ((unsigned long long)__float_as_uint((float)i) << 32) | __float_as_uint((float)threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) c[i] = ((unsigned long long)__float_as_uint(a + i) << 32) | __float_as_uint(a - i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = ((unsigned long long)__float_as_uint(b * i) << 32) | __float_as_uint(b + i);
+    for (int it = 0; it < iters; ++it) {
+        if (ORDER == 0) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[4 * t + j]) : "l"(c[t]), "l"(r[j]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int t = 0; t < 16; ++t)
+                    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[4 * t + j]) : "l"(c[t]), "l"(r[j]));
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 64; ++i) s ^= acc[i];
+    if (s == 0x123456789abcdefull) out[0] = 1.0f;
+}
+
 __global__ void __launch_bounds__(PK_THREADS) peak_lds_kernel(uint32_t *out, int iters)
 {
     extern __shared__ __align__(16) uint8_t pk_smem[];
@@ -82,7 +116,8 @@ __global__ void __launch_bounds__(PK_THREADS) peak_ldg_kernel(const uint4 *__res
 
 }  // namespace
 
-// out (host) [4]: FFMA2 TFLOP/s, FFMA TFLOP/s, shared-memory LDS.128 TB/s, L1-hit LDG.128 TB/s.
+// out (host) [6]: FFMA2 TFLOP/s, FFMA TFLOP/s, shared-memory LDS.128 TB/s, L1-hit LDG.128 TB/s, FFMA2 TFLOP/s with the
+// chain-tile kernel's three-register operand pattern (coefficient-major, row-major order; 8 warps per SM like that kernel).
 // `scratch`: device buffer of at least 1 MiB + 16 bytes (16-byte aligned), read by the L1 probe.  Synchronises the stream.
 extern "C" QBM_API int qbm_probe_onchip_peaks(double *out, void *scratch, size_t scratch_bytes, void *stream)
 {
@@ -128,6 +163,11 @@ extern "C" QBM_API int qbm_probe_onchip_peaks(double *out, void *scratch, size_t
     out[2] = (double)blocks * PK_THREADS * mem_iters * 8 * 16.0 / (ms * 1e-3) * 1e-12;
     if ((rc = timed([&] { peak_ldg_kernel<<<blocks, PK_THREADS, 0, st>>>(reinterpret_cast<const uint4 *>(scratch), uout, mem_iters); }, ms))) return rc;
     out[3] = (double)blocks * PK_THREADS * mem_iters * 8 * 16.0 / (ms * 1e-3) * 1e-12;
+    const int tile_iters = 1 << 12;
+    if ((rc = timed([&] { peak_fma_tile_kernel<0><<<sms, 256, 0, st>>>(fout, tile_iters, 1.0000001f, 1e-9f); }, ms))) return rc;
+    out[4] = (double)sms * 256 * tile_iters * 64 * 2 * 2.0 / (ms * 1e-3) * 1e-12;
+    if ((rc = timed([&] { peak_fma_tile_kernel<1><<<sms, 256, 0, st>>>(fout, tile_iters, 1.0000001f, 1e-9f); }, ms))) return rc;
+    out[5] = (double)sms * 256 * tile_iters * 64 * 2 * 2.0 / (ms * 1e-3) * 1e-12;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return QBM_OK;

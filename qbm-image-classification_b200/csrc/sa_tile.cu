@@ -219,26 +219,12 @@ struct RowRegs {
     uint32_t c;            // dense: shared address of the row's coefficient pairs; sparse: the row's mask word
 };
 
-// rows of a record come in groups of GR per ring slot; `gi` counts groups since launch, `k` rows of this record.
-// `rel` = the slot to hand back to the producer after this row has been applied (the last row of its group), else NONE
-constexpr uint32_t NONE = 0xffffffffu;
+// one coupling row of this thread's columns, from ring position `raddr`
 template <int NS>
-__device__ __forceinline__ void row_fetch(RowRegs<NS> &R, const TileAddr &A, uint32_t &u, uint32_t &gi, uint32_t &k, uint32_t cb_rec,
-                                          uint32_t rm_rec, uint32_t &rel, bool dense)
+__device__ __forceinline__ void row_load(RowRegs<NS> &R, const TileAddr &A, uint32_t raddr)
 {
-    const int a = __ffs(u) - 1;
-    u &= u - 1;
-    const uint32_t j = k & (GR - 1);
-    const uint32_t slot = gi & (NGS - 1);
-    if (j == 0) mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
 #pragma unroll
-    for (int jw = 0; jw < NS / 4; ++jw) R.r[jw] = lds128(A.ring + (slot * GR + j) * A.slot_stride + jw * A.win_stride);
-    if (dense) R.c = cb_rec + (uint32_t)a * (T * 8u);
-    else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(R.c) : "r"(rm_rec + (uint32_t)a * 4u));
-    ++k;
-    const bool last = (j == GR - 1) || (u == 0u);
-    rel = last ? slot : NONE;
-    if (last) { ++gi; k = 0; }
+    for (int jw = 0; jw < NS / 4; ++jw) R.r[jw] = lds128(raddr + jw * A.win_stride);
 }
 
 template <int NS>
@@ -278,36 +264,69 @@ __device__ __forceinline__ void row_apply_sparse(f32x2 (&F2)[NS / 2][T], const R
     }
 }
 
+// The rows of a record arrive through the ring in ascending order of the flipped variable, in groups of up to GR rows per
+// ring slot (`gi` counts groups since launch, exactly as the producer does): one full / empty hand-shake per group, the
+// rows of a group at static offsets -- the per-row bookkeeping is the next set bit of `u` and two address adds.
 template <int NS>
 __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, uint32_t rb,
                                              int lane, uint32_t &gi, uint32_t dense_min)
 {
     const uint32_t cb_rec = A.cbuf + rb * (32u * T * 8u);
     const uint32_t rm_rec = A.rowmask + rb * (32u * 4u);
-    RowRegs<NS> R;
-    uint32_t rel, k = 0;
-    // one row at a time (the other applier warp of the scheduler covers the load latency; a second register buffer costs
-    // more in spilled fields than it hides).  The dense and the sparse loop are kept apart: one loop with both bodies
-    // makes ptxas reconcile the 128 field registers with moves
+    // The dense and the sparse loop are kept apart: one loop with both bodies makes ptxas reconcile the 128 field
+    // registers with moves
     if (count >= dense_min) {
         // dense: nearly every chain flipped nearly every variable -- unconditional FMAs with c in {0, +-2}
         while (u != 0u) {
-            row_fetch<NS>(R, A, u, gi, k, cb_rec, rm_rec, rel, true);
-            row_apply_dense<NS>(F2, R);
-            if (rel != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + rel * 8u);
+            const uint32_t slot = gi & (NGS - 1);
+            const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
+            const uint32_t base = A.ring + slot * (GR * A.slot_stride);
+            mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
+            if (cnt == (uint32_t)GR) {
+                // a full group (nearly all of them while the sweeps are hot): four rows, straight-line
+#pragma unroll
+                for (int j = 0; j < GR; ++j) {
+                    const int a = __ffs(u) - 1;
+                    u &= u - 1;
+                    RowRegs<NS> R;
+                    row_load<NS>(R, A, base + j * A.slot_stride);
+                    R.c = cb_rec + (uint32_t)a * (T * 8u);
+                    row_apply_dense<NS>(F2, R);
+                }
+            } else {
+#pragma unroll 1
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const int a = __ffs(u) - 1;
+                    u &= u - 1;
+                    RowRegs<NS> R;
+                    row_load<NS>(R, A, base + j * A.slot_stride);
+                    R.c = cb_rec + (uint32_t)a * (T * 8u);
+                    row_apply_dense<NS>(F2, R);
+                }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(A.empty + slot * 8u);
+            ++gi;
         }
     } else {
         // sparse: per chain a warp-uniform test of the row's mask word
         while (u != 0u) {
-            row_fetch<NS>(R, A, u, gi, k, cb_rec, rm_rec, rel, false);
-            row_apply_sparse<NS>(F2, R);
-            if (rel != NONE) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive_s(A.empty + rel * 8u);
+            const uint32_t slot = gi & (NGS - 1);
+            const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
+            const uint32_t base = A.ring + slot * (GR * A.slot_stride);
+            mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
+#pragma unroll 1
+            for (uint32_t j = 0; j < cnt; ++j) {
+                const int a = __ffs(u) - 1;
+                u &= u - 1;
+                RowRegs<NS> R;
+                row_load<NS>(R, A, base + j * A.slot_stride);
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(R.c) : "r"(rm_rec + (uint32_t)a * 4u));
+                row_apply_sparse<NS>(F2, R);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(A.empty + slot * 8u);
+            ++gi;
         }
     }
 }

@@ -14,10 +14,11 @@ def measure(device="cuda:0"):
     L = qbm_b200._lib.load()
     torch.cuda.set_device(device)
     scratch = torch.empty((1 << 20) + 64, dtype=torch.uint8, device=device)
-    out = (ctypes.c_double * 4)()
+    out = (ctypes.c_double * 6)()
     qbm_b200._lib.check(L.qbm_probe_onchip_peaks(out, scratch.data_ptr(), scratch.numel(),
                                                  torch.cuda.current_stream().cuda_stream))
-    return {"fp32_ffma2_tflops": out[0], "fp32_ffma_tflops": out[1], "smem_lds128_tbs": out[2], "l1_ldg128_tbs": out[3]}
+    return {"fp32_ffma2_tflops": out[0], "fp32_ffma_tflops": out[1], "smem_lds128_tbs": out[2], "l1_ldg128_tbs": out[3],
+            "fp32_ffma2_3reg_8warps_cmajor_tflops": out[4], "fp32_ffma2_3reg_8warps_rmajor_tflops": out[5]}
 
 
 if __name__ == "__main__":
