@@ -52,13 +52,15 @@ extern "C" QBM_API size_t qbm_sa_workspace_bytes(int n, long long batch_q)
     return (size_t)batch_q * ((size_t)n + 1) * ld * sizeof(float);
 }
 
-// two-phase schedule (chain-tile kernel for the hot sweeps, then one warp per chain): used where it measured faster
-static inline bool sa_two_phase_size(int n) { return n > 1792; }
+// two-phase schedule (chain-tile kernel for the hot sweeps, then one warp per chain): possible from 8 windows on (both
+// kernels then read the same permuted rows), used by default where it measured faster (profiles/r2_two_phase_sizes.log)
+static inline bool sa_two_phase_supported(int n) { return n > 896 && n <= QBM_SA_MAX_N; }
+static inline bool sa_two_phase_size(int n) { return n > QBM_TWO_PHASE_MIN_N; }
 
 extern "C" QBM_API size_t qbm_sa_workspace_bytes_two_phase(int n, long long batch_q, long long num_reads)
 {
     const size_t base = qbm_sa_workspace_bytes(n, batch_q);
-    if (base == 0 || num_reads <= 0 || !sa_two_phase_size(n)) return base;
+    if (base == 0 || num_reads <= 0 || !sa_two_phase_supported(n)) return base;
     const size_t chains = (size_t)batch_q * (size_t)num_reads;
     return base + chains * (size_t)sa_multi_nw(n) * 128 * sizeof(float) + ((chains * sizeof(uint32_t) + 15) / 16) * 16;
 }
@@ -94,8 +96,17 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     float *Jp = reinterpret_cast<float *>(workspace);
     float *hp = Jp + (size_t)batch_q * (size_t)n * (size_t)ld;
 
-    // 8..14 windows run the rotating-window shape, whose rows are stored rotated (sa_warp.cuh)
-    const bool rt = !tile && !multi && nw >= 8 && nw <= 14;
+    // two-phase schedule: in the hot sweeps nearly every chain flips nearly every variable, so the chain-tile kernel (one
+    // fetch of a coupling row for 16 chains, 35 instead of 86 clocks per flip and SM at n = 2048) anneals them and hands every
+    // chain over after the first sweep that accepts less than hot_fraction of its proposals; the warp-per-chain kernel
+    // resumes.  Both kernels follow the same trajectory, so the cut does not change any result.  Needs the larger workspace
+    // (qbm_sa_workspace_bytes_two_phase); flag bit 6 switches it off, flag bit 7 forces it wherever it is supported.
+    const bool two_phase = !tile && !multi && sa_two_phase_supported(n) && (flags & 64u) == 0u &&
+                           (sa_two_phase_size(n) || (flags & 128u) != 0u) && sa_tile_ld(n) == ld &&
+                           workspace_bytes >= qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads);
+    // 8..14 windows run the rotating-window shape, whose rows are stored rotated (sa_warp.cuh); the chain-tile kernel reads
+    // plain rows, so the two-phase schedule resumes with the plain shape
+    const bool rt = !tile && !multi && !two_phase && nw >= 8 && nw <= 14;
     sa_permute_kernel<<<dim3((unsigned)n + 1, (unsigned)batch_q), 128, 0, st>>>(J, h, n, ldj, ld, rt ? nw : 0, Jp, hp);
     QBM_LAUNCH_OK("sa_permute_kernel");
 
@@ -108,23 +119,23 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
     p.fields = nullptr; p.sweeps_done = nullptr; p.hot_fraction = 0.0f;
     if (tile) return sa_tile_launch(p, st);
 
-    // two-phase schedule: in the hot sweeps nearly every chain flips nearly every variable, so the chain-tile kernel (one
-    // fetch of a coupling row for 16 chains) is faster there (58 vs 86 clocks per flip and SM at n = 2048) and the
-    // warp-per-chain kernel everywhere else; the tile kernel hands a chain over after the first sweep that accepts less than
-    // hot_fraction of its proposals.  Both kernels follow the same trajectory, so the cut does not change any result.
-    // Needs the larger workspace (qbm_sa_workspace_bytes_two_phase); flag bit 6 switches it off.
-    if (!multi && sa_two_phase_size(n) && (flags & 64u) == 0u && sa_tile_supported(n) && sa_tile_ld(n) == ld &&
-        workspace_bytes >= qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads)) {
+    if (two_phase) {
         const unsigned pct = (flags >> 16) & 0xffu;
         SaParams hot = p;
         hot.fields = hp + (size_t)batch_q * (size_t)ld;
         hot.sweeps_done = reinterpret_cast<uint32_t *>(hot.fields + (size_t)p.total_chains * (size_t)ld);
-        hot.hot_fraction = pct ? (float)pct / 100.0f : 0.70f;
+        hot.hot_fraction = pct ? (float)pct / 100.0f : 0.55f;
         if (const int rc = sa_tile_launch(hot, st)) return rc;
         // the resuming instantiation (RS) starts from fields / sweeps_done / init instead of computing the initial fields
         p.fields = hot.fields; p.sweeps_done = hot.sweeps_done;
         p.init = states_out;
-        return launch_sa<16, 4, 16, 1, false, false, true, false, false, true>(p, st);
+        switch (nw) {
+            case 8: return launch_sa<8, 4, 16, 1, false, false, true, false, false, true>(p, st);
+            case 10: return launch_sa<10, 4, 16, 1, false, false, true, false, false, true>(p, st);
+            case 12: return launch_sa<12, 4, 16, 1, false, false, true, false, false, true>(p, st);
+            case 14: return launch_sa<14, 4, 16, 1, false, false, true, false, false, true>(p, st);
+            default: return launch_sa<16, 4, 16, 1, false, false, true, false, false, true>(p, st);
+        }
     }
 
     if (multi) return sa_multi_launch(p, nw, st);

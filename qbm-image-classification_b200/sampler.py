@@ -47,7 +47,7 @@ def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_
     ``J`` float32 [batch_q, n, n] (symmetric, zero diagonal), ``h`` float32 [batch_q, n],
     ``betas`` float32 [batch_q, num_betas] or [1, num_betas] / [num_betas] (shared schedule).
     ``flags`` is passed to ``qbm_sa_sample`` (include/qbm_b200.h): 0 = the library's choice -- the warp-per-chain kernel,
-    for n > 1792 preceded by the chain-tile kernel over the hot sweeps (two-phase schedule); 64 = never two-phase,
+    for n > 896 preceded by the chain-tile kernel over the hot sweeps (two-phase schedule); 64 = never two-phase,
     16 / 32 = the chain-tile / chains-per-warp kernel for the whole schedule.  Every choice returns the same states.
     """
     L = _lib.load()
@@ -78,7 +78,7 @@ def sa_sample(J: torch.Tensor, h: torch.Tensor, betas: torch.Tensor, sweeps_per_
             raise ValueError("sa_sample: init_states must be int8 [batch_q, num_reads, n]")
         states = init_states.contiguous().clone() if out is None else out.copy_(init_states)
         return SAResult(states=states, accepted=torch.zeros(2, dtype=torch.int64, device=dev) if count else None)
-    # the larger workspace lets the library run its two-phase schedule where that is faster (n > 1792)
+    # the larger workspace lets the library run its two-phase schedule where that is faster (n > 896)
     need = L.qbm_sa_workspace_bytes_two_phase(n, bq, int(num_reads))
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty((need + 15) // 16 * 4, dtype=torch.float32, device=dev)

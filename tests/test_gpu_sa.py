@@ -219,12 +219,14 @@ def test_sweeps_per_beta_and_single_read(qbm, oracle, cuda, flags):
 
 
 @pytest.mark.parametrize("n,reads,sweeps,pct", [(2048, 20, 60, 0), (1800, 35, 40, 0), (1930, 17, 50, 97), (2048, 16, 30, 1),
-                                                (2000, 5, 25, 100)])
+                                                (2000, 5, 25, 100), (897, 19, 60, 0), (1024, 33, 40, 30), (1290, 17, 40, 0),
+                                                (1536, 20, 50, 0), (1700, 5, 40, 80)])
 def test_two_phase_schedule_is_the_same_trajectory(qbm, oracle, cuda, n, reads, sweeps, pct):
-    """n > 1792: the chain-tile kernel anneals the hot sweeps and hands fields / spins / sweep counters to the warp-per-chain
-    kernel.  Same states as with the hand-over switched off (flag bit 6), for any threshold (bits 16..23: 1 % = the tile
-    kernel does everything, 100 % = it hands over after its first sweep), partial tiles, two problems with their own
-    schedules, host initial states -- and equal to the replay oracle."""
+    """n > 896: the chain-tile kernel anneals the hot sweeps and hands fields / spins / sweep counters to the warp-per-chain
+    kernel (the default above QBM_TWO_PHASE_MIN_N, flag bit 7 elsewhere).  Same states as with the hand-over switched off
+    (flag bit 6), for any threshold (bits 16..23: 1 % = the tile kernel does everything, 100 % = it hands over after its
+    first sweep), partial tiles, two problems with their own schedules, host initial states -- and equal to the replay
+    oracle."""
     Qs = np.stack([random_qubo(n, seed=400 + n + b, scale=1.0 + b) for b in range(2)])
     h, J, _ = qbm.ising.qubo_to_ising(Qs)
     betas, spb = qbm.ising.beta_schedule(qbm.ising.default_beta_range(h, J), sweeps)
@@ -232,7 +234,7 @@ def test_two_phase_schedule_is_the_same_trajectory(qbm, oracle, cuda, n, reads, 
     args = [torch.from_numpy(a).to(cuda) for a in (J32, h32, b32)]
     init = np.stack([qbm.ising.initial_states_numpy(3 + b, reads, n) for b in range(2)])
     for initd in (None, torch.from_numpy(init).to(cuda)):
-        two = qbm.sa_sample(*args, spb, reads, 31, chain_offset=9, init_states=initd, count=True, flags=pct << 16)
+        two = qbm.sa_sample(*args, spb, reads, 31, chain_offset=9, init_states=initd, count=True, flags=128 | (pct << 16))
         one = qbm.sa_sample(*args, spb, reads, 31, chain_offset=9, init_states=initd, count=True, flags=64)
         assert torch.equal(two.states, one.states)
         assert torch.equal(two.accepted, one.accepted)          # accepted flips and proposals add up over the two kernels
