@@ -51,26 +51,41 @@ def workload_name(reads):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's restatement of neal, all host cores, bounded sample
 # ------------------------------------------------------------------------------------------------
+def bench_config(reads):
+    """`config` of the JSON line -- the same keys and values in both arms (driver: same_config)."""
+    return {"workload": workload_name(reads), "reads_per_gpu_per_step": reads, "n": N_VARS, "sweeps": NUM_SWEEPS}
+
+
 def cpu_sa_rate(Q, reads_per_thread, threads, seed=QUBO_SEED):
-    """spin-updates/s of oracle.neal_sample over `threads` concurrent read ranges (ctypes drops the GIL)."""
+    """One call of the reference's sampler on the host cores, as its process pool would run it at best: the dimod / neal glue
+    (BINARY -> SPIN, beta range, schedule, initial states) ONCE per call -- a 1e5-read call amortises it to nothing -- then
+    `threads` threads run the restated cpu_sa.cpp loop (oracle/neal_sa.c; ctypes drops the GIL) on disjoint read ranges.
+    Returns (spin-updates/s, seconds, reads, mean QUBO energy of the reads)."""
     from oracle import oracle as O
-    O.lib()
+    L = O.lib()
     n = Q.shape[0]
-    done = [0] * threads
+    t0 = time.perf_counter()
+    h, _, offset, irow, icol, jval = O.qubo_to_ising(Q)
+    betas, spb = O.beta_schedule(O.default_beta_range(h, jval, irow, icol), NUM_SWEEPS)
+    h = np.ascontiguousarray(h)
+    states = [np.ascontiguousarray(O.initial_states(seed + t, reads_per_thread, n)) for t in range(threads)]
+    energies = [np.zeros(reads_per_thread, dtype=np.float64) for _ in range(threads)]
+    p = lambda a: a.ctypes.data_as(__import__("ctypes").c_void_p)
 
     def work(t):
-        s, _ = O.neal_sample(Q, reads_per_thread, NUM_SWEEPS, seed=seed + t)
-        done[t] = s.shape[0]
+        counters = np.zeros(3, dtype=np.uint64)
+        rc = L.oracle_neal_sa(n, p(h), int(len(jval)), p(irow), p(icol), p(jval), reads_per_thread, p(states[t]),
+                              int(len(betas)), p(betas), int(spb), int(seed + t), p(energies[t]), p(counters))
+        assert rc == 0
 
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-    t0 = time.perf_counter()
     for th in ths:
         th.start()
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    total_reads = sum(done)
-    return total_reads * NUM_SWEEPS * n / dt, dt, total_reads
+    total_reads = threads * reads_per_thread
+    return total_reads * NUM_SWEEPS * n / dt, dt, total_reads, float(np.mean(np.concatenate(energies)) + offset)
 
 
 def run_reference(args):
@@ -79,24 +94,28 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     Q = make_qubo()
-    reads_per_thread = 1
-    for _ in range(args.warmup):
-        cpu_sa_rate(Q, reads_per_thread, cores)
-    t_total, updates = 0.0, 0
-    for _ in range(args.steps):
-        rate, dt, reads = cpu_sa_rate(Q, reads_per_thread, cores)
+    reads_per_thread = args.cpu_reads_per_thread
+    for _ in range(min(args.warmup, 1)):                      # a CPU loop has nothing to warm beyond its caches
+        cpu_sa_rate(Q, 1, cores)
+    t_total, updates, e_means = 0.0, 0, []
+    for i in range(args.steps):
+        rate, dt, reads, e_mean = cpu_sa_rate(Q, reads_per_thread, cores, seed=QUBO_SEED + i * cores)
         t_total += dt
         updates += reads * NUM_SWEEPS * N_VARS
+        e_means.append(e_mean)
     value = updates / t_total
-    sample = f"{cores} threads x {reads_per_thread} read(s) x {NUM_SWEEPS} sweeps at n={N_VARS} per step"
+    sample = (f"{cores} threads x {reads_per_thread} reads x {NUM_SWEEPS} sweeps at n={N_VARS} per step, glue once per step; "
+              "oracle/neal_sa.c = dwave-neal 0.5.9 cpu_sa.cpp restated (float64, xorshift128+)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.reads), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args.reads),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "per_thread": value / cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "mean_energy": float(np.mean(e_means)), "mean_energy_reads": int(args.steps * cores * reads_per_thread),
     }
     print(json.dumps(line), flush=True)
 
@@ -188,6 +207,20 @@ def run_gpu(args):
     counters = torch.zeros(2, dtype=torch.int64, device=dev)
     launches = [0]
     kern_ms = []
+    # on-chip peaks of this device, measured now (FFMA2 / FFMA TFLOP/s, shared-memory and L1 TB/s): the denominators of the
+    # sampler's rooflines; a few milliseconds, outside every timed region
+    onchip = None
+    if rank == 0:
+        import ctypes
+        pk = (ctypes.c_double * 6)()
+        scratch = torch.empty((1 << 20) + 64, dtype=torch.uint8, device=dev)
+        qbm_b200._lib.check(L.qbm_probe_onchip_peaks(pk, scratch.data_ptr(), scratch.numel(), torch.cuda.current_stream().cuda_stream))
+        onchip = {"fp32_ffma2_tflops": pk[0], "fp32_ffma_tflops": pk[1], "smem_lds128_tbs": pk[2], "l1_ldg128_tbs": pk[3],
+                  "fp32_ffma2_3reg_8warps_tflops": pk[4],
+                  "how": "qbm_probe_onchip_peaks: streaming fma.rn.f32x2 / fma.rn.f32 / LDS.128 / L1-hit LDG.128 loops, CUDA events, "
+                         "best of 3; the 3reg figure is FFMA2 with three distinct register operands at 8 warps per SM, the "
+                         "shape of the chain-tile kernel's row update"}
+        del scratch
 
     def step(i, timed):
         # global read index: disjoint ranges per (step, rank)
@@ -201,7 +234,7 @@ def run_gpu(args):
         qbm_b200._lib.check(rc)
         e = qbm_b200.qubo_energies(Qd, out)
         if timed:
-            launches[0] += 4          # sa_permute_kernel, sa_tile_kernel (hot sweeps), sa_kernel, qubo_energy_kernel
+            launches[0] += 4          # sa_permute_kernel, sa_tile_kernel (hot sweeps), sa_kernel (resumed chains), qubo_energy_kernel
             kern_ms.append((ev0, ev1))
         return e
 
@@ -263,6 +296,31 @@ def run_gpu(args):
                           "e2e": {"value": imgs / te2e, "unit": "images/s", "h2d_bytes_per_step": th2d,
                                   "d2h_bytes_per_step": 8}}
 
+    # ---- strong scaling: the config's 1e5-read job as ONE call of the drop-in sampler, reads sharded over the ranks and
+    # all-gathered so that every caller holds all reads (src/qubo/sampler.py:26-33 contract), wall clock on rank 0
+    strong = None
+    if not args.no_strong:
+        total_reads = args.strong_reads
+        smp_obj = qbm_b200.B200SASampler(num_sweeps=NUM_SWEEPS, seed=QUBO_SEED, initial_states_generator="philox", device=dev,
+                                         process_group=dist.group.WORLD if distributed else None)
+        barrier()
+        w0 = time.perf_counter()
+        allreads = smp_obj.sample_Q(Q, total_reads)
+        torch.cuda.synchronize()
+        barrier()
+        strong_s = time.perf_counter() - w0
+        assert allreads.shape == (total_reads, n)
+        if distributed:
+            tt = torch.tensor([strong_s], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            strong_s = float(tt[0])
+        strong = {"reads": total_reads, "n_gpus": world, "wall_s": strong_s,
+                  "value": total_reads * NUM_SWEEPS * n / strong_s, "unit": UNIT, "scaling": "strong",
+                  "api": "B200SASampler(num_sweeps=1000, process_group=WORLD).sample_Q(Q, reads): H2D of Q, K0, sharded reads, "
+                         "NCCL all-gather of the int8 samples, D2H and the float32 [reads, n] result of the boundary on every rank",
+                  "result_bytes_per_rank": int(allreads.nbytes)}
+        del allreads
+
     if distributed:
         t = torch.tensor([ms, e2e_s, float(acc), float(prop), sa_ms], dtype=torch.float64, device=dev)
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -277,8 +335,10 @@ def run_gpu(args):
         assert abs(prop_all - total_updates) < 0.5, (prop_all, total_updates)
         value = total_updates / (ms * 1e-3)
         e2e_value = float(world) * e2e_steps * R * NUM_SWEEPS * n / e2e_s
-        # roofline of the dominant kernel (sa_kernel), per launch on one GPU: algorithmic on-chip bytes
-        # 4nA + 4P (coupling row per accepted flip + one field per proposal) and flops 2nA
+        # roofline of one qbm_sa_sample launch on one GPU (chain-tile kernel over the hot sweeps + resumed warp-per-chain
+        # kernel): algorithmic work of SURVEY.md 8d with A accepted flips and P proposals counted by the kernels themselves --
+        # flops 2nA (one FMA per local field per accepted flip), on-chip bytes 4nA + 4P (a coupling row per accepted flip, a
+        # field per proposal), compulsory HBM bytes 4n^2 + R(n + 4) + 8R
         A = acc_all / (world * args.steps); P = prop_all / (world * args.steps)
         alg_bytes = 4.0 * n * A + 4.0 * P
         alg_flops = 2.0 * n * A
@@ -288,47 +348,55 @@ def run_gpu(args):
                 peaks = json.load(f)
         except OSError:
             pass
-        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-        sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-        l1_peak = 128.0 * sm_count * sm_mhz * 1e6 / 1e9           # GB/s: 128 B/clk/SM L1/shared pipe
-        fp32_peak = 2.0 * 128.0 * sm_count * sm_mhz * 1e6 / 1e12  # TFLOP/s
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / (sa_ms * 1e-3) / 1e9
+        fp32_peak = onchip["fp32_ffma2_tflops"]
+        l1_peak = onchip["l1_ldg128_tbs"] * 1e3                   # GB/s
+        achieved_tf = alg_flops / (sa_ms * 1e-3) / 1e12
         hbm_bytes = 4.0 * n * n + R * (n + 4) + 8.0 * R
-        traffic = None
+        traffic, traffic_note = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-                traffic = json.load(f).get("sa_kernel_dram_bytes_per_launch")
-        except (OSError, ValueError):
+                tj = json.load(f)
+            # measured per launch of `reads` reads: the coupling matrix once per kernel + per-chain hand-over / state bytes
+            per_chain = (tj["dram_bytes_per_launch"] - tj["dram_bytes_fixed"]) / tj["reads"]
+            traffic = tj["dram_bytes_fixed"] + per_chain * R
+            traffic_note = (f"ncu dram__bytes_read.sum + dram__bytes_write.sum of the two sampler kernels at {tj['reads']} reads "
+                            f"({tj['source']})" + ("" if tj["reads"] == R else f", per-chain part scaled to {R} reads"))
+        except (OSError, ValueError, KeyError):
             pass
         roofline = {
-            "kernel": "sa_tile_kernel<8,384> (hot sweeps) + sa_kernel<16,4,16,1,...,RS> (rest): one qbm_sa_sample launch",
-            "bound": "l1-shared-pipe",
-            "bound_note": "neither of the contract's two rooflines applies: the sampler consumes one coupling row per accepted "
-                          "flip on chip (ncu of the warp-per-chain kernel: l1tex data pipe 78 %, DRAM 0.001 %, no tensor "
-                          "work); 'achieved' counts the ALGORITHMIC bytes 4nA + 4P of SURVEY.md 8d, of which the chain-tile "
-                          "kernel really moves 1/16 in the hot sweeps (one row fetch serves 16 chains), so the fraction is "
-                          "against what one warp per chain would have to stream through L1; HBM under 'hbm', FP32 under 'fp32'",
-            "achieved": achieved, "peak": l1_peak,
-            "unit": "GB/s", "frac": achieved / l1_peak, "traffic": traffic,
-            "peak_source": f"derived: 128 B/clk/SM x {sm_count} SMs x {sm_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
-                           "the kernel streams coupling rows from L1, not HBM (SURVEY.md 8d)",
-            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sa_ms,
-            "fp32": {"achieved_tflops": alg_flops / (sa_ms * 1e-3) / 1e12, "peak_tflops": fp32_peak,
-                     "frac": alg_flops / (sa_ms * 1e-3) / 1e12 / fp32_peak},
+            "kernel": "sa_tile_kernel<8> (hot sweeps, ~97 % of the flips) + sa_kernel<16,4,16,1,...,RS> (resumed chains): one "
+                      "qbm_sa_sample launch",
+            "bound": "fp32-pipe",
+            "bound_note": "neither of the contract's two rooflines applies: the sampler spends one FMA per local field per "
+                          "accepted flip and reads its coupling rows on chip (DRAM < 0.1 % of peak, no tensor work).  The "
+                          "chain-tile kernel fetches a row once for 16 chains, so the unit that bounds the launch is the FP32 "
+                          "FMA pipe: achieved = 2nA flop / launch time against the FFMA2 rate measured on this device.  "
+                          "Secondary: 'l1' = the ALGORITHMIC bytes 4nA + 4P against the measured L1 rate (what one warp per chain "
+                          "would have to stream; the tile kernel moves 1/16 of it), 'hbm' = compulsory bytes against "
+                          "MEASURED_PEAKS.json",
+            "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak,
+            "traffic": traffic, "traffic_note": traffic_note,
+            "peak_source": "measured in this run by qbm_probe_onchip_peaks (fma.rn.f32x2 streaming loop)",
+            "algorithmic_flops_per_launch": alg_flops, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sa_ms,
+            "frac_of_3reg_ffma2_rate": achieved_tf / onchip["fp32_ffma2_3reg_8warps_tflops"],
+            "l1": {"achieved_gbs": alg_bytes / (sa_ms * 1e-3) / 1e9, "peak_gbs": l1_peak,
+                   "frac": alg_bytes / (sa_ms * 1e-3) / 1e9 / l1_peak, "peak_source": "measured in this run (L1-hit LDG.128 loop)"},
             "hbm": {"compulsory_bytes_per_launch": hbm_bytes, "achieved_gbs": hbm_bytes / (sa_ms * 1e-3) / 1e9,
                     "peak_gbs": hbm_peak, "frac": hbm_bytes / (sa_ms * 1e-3) / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
             "accepted_fraction": A / P,
+            "onchip_peaks": onchip,
         }
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rpt = 2
-            rate, dt, reads = cpu_sa_rate(Q, rpt, cores)
-            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"{cores} threads x {rpt} reads x {NUM_SWEEPS} sweeps at n={n} ({dt:.1f} s); "
-                             "oracle/neal_sa.c = dwave-neal 0.5.9 cpu_sa.cpp restated (float64, xorshift128+)"}
+            rpt = args.cpu_reads_per_thread
+            rate, dt, reads, cpu_e = cpu_sa_rate(Q, rpt, cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "per_thread": rate / cores,
+                   "sample": f"{cores} threads x {rpt} reads x {NUM_SWEEPS} sweeps at n={n}, glue once ({dt:.1f} s); "
+                             "oracle/neal_sa.c = dwave-neal 0.5.9 cpu_sa.cpp restated (float64, xorshift128+)",
+                   "mean_energy": cpu_e, "mean_energy_reads": reads}
         if train is not None and world == 1 and not args.no_cpu_baseline:
             import bench_train as BT
             for cfg, images in (("c1", 2 * cores), ("c3", cores), ("c5", cores)):
@@ -344,18 +412,20 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(R), "reads_per_gpu_per_step": R, "n": n, "sweeps": NUM_SWEEPS,
-                       "beta_range": br[0].tolist(), "initial_states": "philox",
-                       "l2_policy": "outputs (20 MB states per step) and the 16.8 MB coupling matrix are re-read "
-                                    "from L2/L1 by design; per-step working set differs by read range, no L2 flush needed "
-                                    "because the kernel is on-chip-bandwidth bound (HBM frac < 0.1%)",
-                       "mean_energy_last_step": e_mean},
+            "config": bench_config(R),
+            "details": {"beta_range": br[0].tolist(), "initial_states": "philox",
+                        "l2_policy": "outputs (20 MB states per step) and the 16.8 MB coupling matrix are re-read "
+                                     "from L2/L1 by design; per-step working set differs by read range, no L2 flush needed "
+                                     "because the kernel is FP32-pipe bound (HBM frac < 0.1%)",
+                        "mean_energy_last_step": e_mean, "mean_energy_reads": R,
+                        "mean_energy_cpu_port": cpu["mean_energy"] if cpu else None},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "qbm_b200.sample_qubo_batch (under B200SASampler.sample_Q)"},
             "gpu_launches": launches[0] * 1,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clk,
+            "strong": strong,
             "train": train,
         }
         print(json.dumps(line), flush=True)
@@ -374,6 +444,10 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the QBM / RBM training-throughput legs")
     ap.add_argument("--train-steps", type=int, default=3, help="timed minibatches per training leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi during the timed region")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling block (one 1e5-read sample_Q call)")
+    ap.add_argument("--strong-reads", type=int, default=100000, help="reads of the strong-scaling call (the C4 job: 1e5)")
+    ap.add_argument("--cpu-reads-per-thread", type=int, default=2,
+                    help="reads each host thread anneals per CPU step (reference arm and cpu_baseline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

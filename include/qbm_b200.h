@@ -173,6 +173,24 @@ int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, floa
                      unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
                      void *stream);
 
+/* Data-parallel form of the two steps (minibatch rows sharded over the GPUs, ONE all-reduce of the
+ * parameter-shaped statistics, identical update on every rank).  The gradient variants leave the parameters untouched and
+ * write the raw sums of their shard into one flat buffer of qbm_rbm_grad_count(V, H, C) floats, 16-byte aligned:
+ *   [ dW (V x ld4(H)) | dU (C x ld4(H)) | db_v (V) | db_h (H) | db_c (C) | loss sum (1) ]   (segments padded to 4 floats)
+ * which the caller all-reduces (sum) as it is; qbm_rbm_apply_grad then performs update_weights (ref: :88-99):
+ * param += scale * grad with scale = factor * lr / global batch, the three biases -= sparse_constant, W^T refreshed in
+ * the same pass, loss_out (nullable) = loss sum * loss_scale.
+ */
+size_t qbm_rbm_grad_count(int V, int H, int C);
+int qbm_rbm_disc_grad(const float *Wt, const float *U, const float *b_h, const float *b_c, const float *x, const int *y,
+                      int B, int V, int H, int C, float *grad, float *probs, int *pred, void *workspace,
+                      size_t workspace_bytes, void *stream);
+int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h, const float *b_c,
+                     const float *v0, const int *y0, int B, int V, int H, int C, unsigned long long seed, unsigned int step,
+                     float *grad, void *workspace, size_t workspace_bytes, void *stream);
+int qbm_rbm_apply_grad(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *grad, int V, int H,
+                       int C, float scale, float sparse_constant, float *loss_out, float loss_scale, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * K7 / K8 / K9  the Disc_QBM training step around the sampler, one launch each per minibatch (float64).
  * Parameters live in ONE flat buffer, which is also the layout of the error buffer:

@@ -96,7 +96,8 @@ __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__
 __global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U,
                                                              long long ldu, float *__restrict__ b_h, const float *__restrict__ P,
                                                              long long ldp, const int *__restrict__ y, const float *__restrict__ Dt,
-                                                             long long lddt, int B, int H, float scale, float sparse)
+                                                             long long lddt, int B, int H, float scale, float sparse,
+                                                             float *__restrict__ gU, float *__restrict__ gbh)
 {
     __shared__ float red[2][8][33];
     const int hx = threadIdx.x & 31, sy = threadIdx.x >> 5;
@@ -119,15 +120,21 @@ __global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__res
         float gs = 0.0f, gbs = 0.0f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) { gs += red[0][k][hx]; gbs += red[1][k][hx]; }
-        U[(size_t)c * ldu + h] = u + scale * gs;
-        if (c == 0) b_h[h] = b_h[h] + scale * gbs - sparse;
+        if (gU != nullptr) {                      // gradient mode (data-parallel steps): the raw sums, parameters untouched
+            gU[(size_t)c * ldu + h] = gs;
+            if (c == 0) gbh[h] = gbs;
+        } else {
+            U[(size_t)c * ldu + h] = u + scale * gs;
+            if (c == 0) b_h[h] = b_h[h] + scale * gbs - sparse;
+        }
     }
 }
 
 // class-bias update, visible-bias decay, loss (CrossEntropyLoss applied to probabilities, :142) and argmax
 __global__ void rbm_disc_finish_kernel(float *__restrict__ b_c, float *__restrict__ b_v, const float *__restrict__ P,
                                        long long ldp, const int *__restrict__ y, int B, int C, int V, float scale,
-                                       float sparse, int *__restrict__ pred, float *__restrict__ loss, int update)
+                                       float sparse, int *__restrict__ pred, float *__restrict__ loss, int update,
+                                       float *__restrict__ gbc = nullptr)
 {
     __shared__ float red[256];
     const int tid = threadIdx.x;
@@ -142,8 +149,16 @@ __global__ void rbm_disc_finish_kernel(float *__restrict__ b_c, float *__restric
     red[tid] = l;
     __syncthreads();
     for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-    if (tid == 0 && loss != nullptr) loss[0] = red[0] / (float)B;
+    if (tid == 0 && loss != nullptr) loss[0] = (update == 2) ? red[0] : red[0] / (float)B;     // gradient mode: the sum
     if (!update) return;
+    if (update == 2) {
+        if (tid < C) {
+            float g = 0.0f;
+            for (int b = 0; b < B; ++b) g += (y[b] == tid ? 1.0f : 0.0f) - P[(size_t)b * ldp + tid];
+            gbc[tid] = g;
+        }
+        return;
+    }
     if (tid < C) {
         float g = 0.0f;
         for (int b = 0; b < B; ++b) g += (y[b] == tid ? 1.0f : 0.0f) - P[(size_t)b * ldp + tid];
@@ -212,7 +227,7 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
                                                                  const int *__restrict__ y0, const int *__restrict__ y1,
                                                                  float *__restrict__ U, long long ldu, float *__restrict__ b_v,
                                                                  float *__restrict__ b_h, float *__restrict__ b_c, int B, int V,
-                                                                 int H, int C, float scale, float sparse)
+                                                                 int H, int C, float scale, float sparse, int grad_mode)
 {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
         float g = 0.0f;
         for (int b = lane; b < B; b += 32) g += v0t[(size_t)i * ldvt + b] - v1t[(size_t)i * ldvt + b];
         g = warp_sum(g);
-        if (lane == 0) b_v[i] = b_v[i] + scale * g - sparse;
+        if (lane == 0) b_v[i] = grad_mode ? g : b_v[i] + scale * g - sparse;
     }
     if (i < H) {
         float gh = 0.0f, gu[MAXC];
@@ -235,12 +250,12 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
                 if (c < C) gu[c] += (c0 == c ? a0 : 0.0f) - (c1 == c ? a1 : 0.0f);
         }
         gh = warp_sum(gh);
-        if (lane == 0) b_h[i] = b_h[i] + scale * gh - sparse;
+        if (lane == 0) b_h[i] = grad_mode ? gh : b_h[i] + scale * gh - sparse;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             if (c < C) {
                 const float t = warp_sum(gu[c]);
-                if (lane == 0) U[(size_t)c * ldu + i] += scale * t;
+                if (lane == 0) U[(size_t)c * ldu + i] = grad_mode ? t : U[(size_t)c * ldu + i] + scale * t;
             }
         }
     }
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
         float g = 0.0f;
         for (int b = lane; b < B; b += 32) g += (y0[b] == i ? 1.0f : 0.0f) - (y1[b] == i ? 1.0f : 0.0f);
         g = warp_sum(g);
-        if (lane == 0) b_c[i] = b_c[i] + scale * g - sparse;
+        if (lane == 0) b_c[i] = grad_mode ? g : b_c[i] + scale * g - sparse;
     }
 }
 
@@ -282,6 +297,71 @@ Ws carve(void *workspace, int B, int V, int H, int C)
     w.v1t = take((size_t)V * lB); w.p1t = take((size_t)H * lB); w.pc = take((size_t)B * lC);
     w.y1 = reinterpret_cast<int *>(take(lB));
     return w;
+}
+
+// ---- data-parallel steps: gradients in ONE flat buffer (all-reduced as it is), then one fused apply --------------
+// layout (floats; every segment starts at a multiple of 4): gW [V, ld4(H)] | gU [C, ld4(H)] | gb_v [V] | gb_h [H] | gb_c [C] | loss sum [1]
+struct Grad {
+    float *gW, *gU, *gbv, *gbh, *gbc, *loss;
+};
+size_t grad_floats(int V, int H, int C)
+{
+    const size_t lH = ld4(H);
+    return (size_t)V * lH + (size_t)C * lH + ld4(V) + ld4(H) + ld4(C) + 4;
+}
+Grad grad_carve(float *g, int V, int H, int C)
+{
+    const size_t lH = ld4(H);
+    Grad r;
+    r.gW = g; g += (size_t)V * lH;
+    r.gU = g; g += (size_t)C * lH;
+    r.gbv = g; g += ld4(V);
+    r.gbh = g; g += ld4(H);
+    r.gbc = g; g += ld4(C);
+    r.loss = g;
+    return r;
+}
+
+// W += scale gW and W^T refreshed in the same pass (32 x 32 tiles through shared memory); the blocks past the W tiles
+// apply the small parameters (param += scale g, the three biases then -= sparse: ClassificationRBM.py:88-99)
+__global__ void __launch_bounds__(256) rbm_apply_kernel(float *__restrict__ W, float *__restrict__ Wt, float *__restrict__ U,
+                                                       float *__restrict__ b_v, float *__restrict__ b_h, float *__restrict__ b_c,
+                                                       const float *__restrict__ gW, const float *__restrict__ gU,
+                                                       const float *__restrict__ gbv, const float *__restrict__ gbh,
+                                                       const float *__restrict__ gbc, const float *__restrict__ gloss, int V, int H,
+                                                       int C, long long lH, long long lV, float scale, float sparse,
+                                                       float *__restrict__ loss_out, float loss_scale, int tiles_x, int tiles)
+{
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if ((int)blockIdx.x < tiles) {
+        const int h0 = ((int)blockIdx.x % tiles_x) * 32, v0 = ((int)blockIdx.x / tiles_x) * 32;
+        for (int i = ty; i < 32; i += 8) {
+            const int v = v0 + i, h = h0 + tx;
+            float w = 0.0f;
+            if (v < V && h < H) {
+                w = W[(size_t)v * lH + h] + scale * gW[(size_t)v * lH + h];
+                W[(size_t)v * lH + h] = w;
+            }
+            tile[i][tx] = w;
+        }
+        __syncthreads();
+        for (int i = ty; i < 32; i += 8) {
+            const int h = h0 + i, v = v0 + tx;
+            if (h < H && v < V) Wt[(size_t)h * lV + v] = tile[tx][i];
+        }
+        return;
+    }
+    const int e0 = ((int)blockIdx.x - tiles) * 256 + threadIdx.x;
+    const int stride = ((int)gridDim.x - tiles) * 256;
+    for (int e = e0; e < C * H; e += stride) {
+        const int c = e / H, h = e % H;
+        U[(size_t)c * lH + h] += scale * gU[(size_t)c * lH + h];
+    }
+    for (int v = e0; v < V; v += stride) b_v[v] = b_v[v] + scale * gbv[v] - sparse;
+    for (int h = e0; h < H; h += stride) b_h[h] = b_h[h] + scale * gbh[h] - sparse;
+    for (int c = e0; c < C; c += stride) b_c[c] = b_c[c] + scale * gbc[c] - sparse;
+    if (e0 == 0 && loss_out != nullptr) loss_out[0] = gloss[0] * loss_scale;
 }
 
 int check_dims(const char *who, int B, int V, int H, int C)
@@ -389,7 +469,7 @@ extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b
     if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
     // class weights / hidden bias (reads the pre-update A, U), then class bias, loss, argmax
     rbm_disc_update_kernel<<<dim3((H + 31) / 32, C), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
-                                                                   sparse_constant);
+                                                                   sparse_constant, nullptr, nullptr);
     QBM_LAUNCH_OK("rbm_disc_update_kernel");
     rbm_disc_finish_kernel<<<1, 256, 0, st>>>(b_c, b_v, probs, lC, y, B, C, V, scale, sparse_constant, pred, loss, 1);
     QBM_LAUNCH_OK("rbm_disc_finish_kernel");
@@ -434,7 +514,7 @@ extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_
     // small parameters, then W += scale (v0^T ph0 - v1^T ph1) fused into two GEMM epilogues, then W^T
     const int mx = (V > H ? V : H) > C ? (V > H ? V : H) : C;
     rbm_cd_small_update_kernel<<<(mx + 7) / 8, 256, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, U, lH, b_v, b_h,
-                                                                b_c, B, V, H, C, scale, sparse_constant);
+                                                                b_c, B, V, H, C, scale, sparse_constant, 0);
     QBM_LAUNCH_OK("rbm_cd_small_update_kernel");
     EpiParams g1 = {};
     g1.C = W; g1.ldc = lH; g1.Cin = W; g1.ldcin = lH; g1.alpha = scale; g1.beta = 1.0f;
@@ -442,4 +522,100 @@ extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_
     g1.alpha = -scale;
     if (int rc = qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st)) return rc;
     return transpose(W, lH, Wt, lV, V, H, st);
+}
+
+// ---- gradient variants of the two steps + the fused apply: what the data-parallel trainers run ------------------------
+// (shard gradient -> ONE all-reduce of the flat buffer -> identical apply on every rank)
+extern "C" QBM_API size_t qbm_rbm_grad_count(int V, int H, int C)
+{
+    if (V < 1 || H < 1 || C < 1) return 0;
+    return grad_floats(V, H, C);
+}
+
+// R4 (:101-146) without R5: the raw gradient sums of this shard (dW = x^T D, dU, db_h, db_c, db_v = 0) and the loss SUM
+extern "C" QBM_API int qbm_rbm_disc_grad(const float *Wt, const float *U, const float *b_h, const float *b_c, const float *x,
+                                         const int *y, int B, int V, int H, int C, float *grad, float *probs, int *pred,
+                                         void *workspace, size_t workspace_bytes, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_disc_grad", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(Wt && U && b_h && b_c && x && y && grad && probs && workspace, "qbm_rbm_disc_grad: null pointer argument");
+    QBM_CHECK_ARG((reinterpret_cast<uintptr_t>(grad) & 15u) == 0, "qbm_rbm_disc_grad: grad must be 16-byte aligned");
+    if (workspace_bytes < qbm_rbm_workspace_bytes(B, V, H, C)) { qbm_set_error("qbm_rbm_disc_grad: workspace too small"); return QBM_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = carve(workspace, B, V, H, C);
+    const Grad g = grad_carve(grad, V, H, C);
+    const long long lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    EpiParams e1 = {};
+    e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB);
+    QBM_LAUNCH_OK("rbm_rows_kernel");
+    if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
+    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C), 256, 0, st>>>(w.A, lH, const_cast<float *>(U), lH, nullptr, probs, lC, y, w.Dt,
+                                                                   lB, B, H, 0.0f, 0.0f, g.gU, g.gbh);
+    QBM_LAUNCH_OK("rbm_disc_update_kernel");
+    rbm_disc_finish_kernel<<<1, 256, 0, st>>>(nullptr, nullptr, probs, lC, y, B, C, V, 0.0f, 0.0f, pred, g.loss, 2, g.gbc);
+    QBM_LAUNCH_OK("rbm_disc_finish_kernel");
+    QBM_CUDA_OK(cudaMemsetAsync(g.gbv, 0, (size_t)V * sizeof(float), st));        // the discriminative gradient has no b_v term (:138)
+    EpiParams e2 = {};
+    e2.C = g.gW; e2.ldc = lH; e2.alpha = 1.0f;
+    return qbm_gemm_tf32_launch(w.xt, lB, w.Dt, lB, V, H, B, e2, st);
+}
+
+// CD-1 (the composition of :43-60) without R5: dW = v0^T ph0 - v1^T ph1, dU, db_v, db_h, db_c of this shard
+extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h,
+                                        const float *b_c, const float *v0, const int *y0, int B, int V, int H, int C,
+                                        unsigned long long seed, unsigned int step, float *grad, void *workspace,
+                                        size_t workspace_bytes, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_cd1_grad", B, V, H, C)) return rc;
+    QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && v0 && y0 && grad && workspace, "qbm_rbm_cd1_grad: null pointer argument");
+    QBM_CHECK_ARG((reinterpret_cast<uintptr_t>(grad) & 15u) == 0, "qbm_rbm_cd1_grad: grad must be 16-byte aligned");
+    if (workspace_bytes < qbm_rbm_workspace_bytes(B, V, H, C)) { qbm_set_error("qbm_rbm_cd1_grad: workspace too small"); return QBM_EWORKSPACE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    Ws w = carve(workspace, B, V, H, C);
+    const Grad g = grad_carve(grad, V, H, C);
+    const long long lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
+    EpiParams e = {};
+    e.C = w.p0; e.ldc = lH; e.Ct = w.p0t; e.ldct = lB; e.S = w.h0; e.lds = lH; e.bias_n = b_h; e.rowtab = U; e.ridx = y0;
+    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u;
+    if (int rc = qbm_gemm_tf32_launch(v0, lV, Wt, lV, B, H, V, e, st)) return rc;
+    EpiParams e2 = {};
+    e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
+    e2.stream = step * 4u + 1u;
+    if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u);
+    QBM_LAUNCH_OK("rbm_class_kernel");
+    EpiParams e3 = {};
+    e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
+    if (int rc = qbm_gemm_tf32_launch(w.v1, lV, Wt, lV, B, H, V, e3, st)) return rc;
+    if (int rc = transpose(v0, lV, w.xt, lB, B, V, st)) return rc;
+    const int mx = (V > H ? V : H) > C ? (V > H ? V : H) : C;
+    rbm_cd_small_update_kernel<<<(mx + 7) / 8, 256, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, g.gU, lH, g.gbv, g.gbh,
+                                                                g.gbc, B, V, H, C, 0.0f, 0.0f, 1);
+    QBM_LAUNCH_OK("rbm_cd_small_update_kernel");
+    QBM_CUDA_OK(cudaMemsetAsync(g.loss, 0, 4 * sizeof(float), st));
+    EpiParams g1 = {};
+    g1.C = g.gW; g1.ldc = lH; g1.alpha = 1.0f;
+    if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.p0t, lB, V, H, B, g1, st)) return rc;
+    g1.Cin = g.gW; g1.ldcin = lH; g1.alpha = -1.0f; g1.beta = 1.0f;
+    return qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st);
+}
+
+// R5 (:88-99) on the (all-reduced) gradient buffer: param += scale * grad with scale = factor * lr / global batch, the three
+// biases -= sparse_constant, W^T refreshed in the same pass; loss_out (nullable) = loss sum * loss_scale
+extern "C" QBM_API int qbm_rbm_apply_grad(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *grad,
+                                          int V, int H, int C, float scale, float sparse_constant, float *loss_out,
+                                          float loss_scale, void *stream)
+{
+    if (int rc = check_dims("qbm_rbm_apply_grad", 1, V, H, C)) return rc;
+    QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && grad, "qbm_rbm_apply_grad: null pointer argument");
+    const Grad g = grad_carve(const_cast<float *>(grad), V, H, C);
+    const int tx = (H + 31) / 32, ty = (V + 31) / 32;
+    const int tiles = tx * ty;
+    rbm_apply_kernel<<<tiles + 8, 256, 0, (cudaStream_t)stream>>>(W, Wt, U, b_v, b_h, b_c, g.gW, g.gU, g.gbv, g.gbh, g.gbc, g.loss, V,
+                                                                   H, C, ld4(H), ld4(V), scale, sparse_constant, loss_out,
+                                                                   loss_scale, tx, tiles);
+    QBM_LAUNCH_OK("rbm_apply_kernel");
+    return QBM_OK;
 }

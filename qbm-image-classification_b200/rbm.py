@@ -75,6 +75,7 @@ class B200ClassificationRBM:
         self.class_bias = torch.zeros(C, device=self.device)
         self._ws = None
         self._ws_key = None
+        self._grad = None
         self._step = 0
         self.acc_per_epoch_list = []
         self.auc_per_epoch_list = []
@@ -156,32 +157,21 @@ class B200ClassificationRBM:
         import torch.distributed as dist
         return dist.get_rank(self.pg)
 
-    def _data_parallel(self, run, B_local, global_batch, loss):
-        """The step kernels update the parameters in place with gradient sums scaled by lr / B.  For a sharded
-        minibatch every rank runs the step on its shard with lr * B_local / B_global (and no decay), the parameter
-        deltas are all-reduced (sum) and applied to the pre-step parameters -- the update of the whole minibatch
-        -- then the decay (sparse_constant) is applied once and W^T is refreshed."""
-        import torch.distributed as dist
-        gb = float(global_batch if global_batch is not None else B_local * self._world())
-        params = [self._W, self._U, self.visible_bias, self.hidden_bias, self.class_bias]
-        before = [t.clone() for t in params]
-        run(self.learning_rate * B_local / gb, 0.0)
-        parts = [(c - b).reshape(-1) for c, b in zip(params, before)]
-        if loss is not None:
-            parts.append(loss.reshape(1) * (B_local / gb))
-        delta = torch.cat(parts)
-        dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=self.pg)
-        pos = 0
-        for c, b in zip(params, before):
-            c.copy_(b + delta[pos:pos + c.numel()].view_as(c))
-            pos += c.numel()
-        if loss is not None:
-            loss.copy_(delta[pos:pos + 1])
-        if self.sparse_constant:
-            for t in (self.visible_bias, self.hidden_bias, self.class_bias):
-                t -= self.sparse_constant
-        self._Wt.zero_()
-        self._Wt[:, :self.num_visible] = self._W[:, :self.num_hidden].t()
+    def _grad_buffer(self):
+        """The flat gradient buffer of the data-parallel steps ([dW | dU | db_v | db_h | db_c | loss sum], include/qbm_b200.h):
+        written by the gradient kernels, all-reduced as it is, consumed by the fused apply."""
+        if getattr(self, "_grad", None) is None:
+            n = _lib.load().qbm_rbm_grad_count(self.num_visible, self.num_hidden, self.num_classes)
+            self._grad = torch.zeros(n, dtype=torch.float32, device=self.device)
+        return self._grad
+
+    def _apply_grad(self, grad, global_batch, factor, loss):
+        """update_weights (:88-99) from the all-reduced gradient sums: one fused launch (W, W^T, U, the biases, the loss)."""
+        L = _lib.load()
+        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(),
+                   self.num_visible, self.num_hidden, self.num_classes, float(factor * self.learning_rate / global_batch),
+                   float(self.sparse_constant), loss.data_ptr() if loss is not None else None, float(1.0 / global_batch))
 
     # ---- Gibbs primitives (:43-60) --------------------------------------------------------------------
     def sample_hidden(self, visible_activations, class_activations):
@@ -238,16 +228,22 @@ class B200ClassificationRBM:
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
         ws = self._workspace(B)
 
-        def run(lr, sparse):
+        if self.pg is None:
             self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
                        self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), x.data_ptr(),
-                       y.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(lr), float(factor),
-                       float(sparse), probs.data_ptr(), pred.data_ptr(), loss.data_ptr(), ws.data_ptr(), ws.numel() * 4)
-
-        if self.pg is None:
-            run(self.learning_rate, self.sparse_constant)
+                       y.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(self.learning_rate),
+                       float(factor), float(self.sparse_constant), probs.data_ptr(), pred.data_ptr(), loss.data_ptr(),
+                       ws.data_ptr(), ws.numel() * 4)
         else:
-            self._data_parallel(run, B, global_batch, loss)
+            # data-parallel minibatch: the gradient sums of this shard into the flat buffer, ONE all-reduce, one fused apply
+            import torch.distributed as dist
+            grad = self._grad_buffer()
+            self._call(L.qbm_rbm_disc_grad, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
+                       self.class_bias.data_ptr(), x.data_ptr(), y.data_ptr(), B, self.num_visible, self.num_hidden,
+                       self.num_classes, grad.data_ptr(), probs.data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+            gb = float(global_batch if global_batch is not None else B * self._world())
+            self._apply_grad(grad, gb, factor, loss)
         self._step += 1
         return loss[0], pred.to(torch.int64), probs[:, :self.num_classes]
 
@@ -261,16 +257,23 @@ class B200ClassificationRBM:
         # sharded minibatches draw from disjoint Philox streams: the step counter is offset by the rank
         stream = (self._step * self._world() + self._rank()) & 0x3FFFFFFF
 
-        def run(lr, sparse):
+        if self.pg is None:
             self._call(L.qbm_rbm_cd1_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
                        self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(),
-                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(lr), float(sparse),
-                       ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream), ws.data_ptr(), ws.numel() * 4)
-
-        if self.pg is None:
-            run(self.learning_rate, self.sparse_constant)
+                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(self.learning_rate),
+                       float(self.sparse_constant), ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream),
+                       ws.data_ptr(), ws.numel() * 4)
         else:
-            self._data_parallel(run, B, global_batch, None)
+            import torch.distributed as dist
+            grad = self._grad_buffer()
+            self._call(L.qbm_rbm_cd1_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(),
+                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes,
+                       ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream), grad.data_ptr(), ws.data_ptr(),
+                       ws.numel() * 4)
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+            gb = float(global_batch if global_batch is not None else B * self._world())
+            self._apply_grad(grad, gb, 1.0, None)
         self._step += 1
 
     def predict(self, input_data):

@@ -83,6 +83,37 @@ def _worker(rank, world, port, out_dir):
         one = qbm_b200.B200SASampler(num_sweeps=200, seed=9, device=dev).sample_Q(Q, 33)
         both = qbm_b200.B200SASampler(num_sweeps=200, seed=9, device=dev, process_group=pg).sample_Q(Q, 33)
         res["sa_gather"] = float(np.abs(one - both).max()) + (0.0 if both.shape == (33, 150) else 1.0)
+        # K2 on the shards + all-gather of the energies: samples AND energies of the sharded call equal the single-GPU call
+        s1, e1, _ = qbm_b200.sample_qubo_batch(Q, 33, 200, seed=9, device=dev, return_energy=True)
+        s2, e2, _ = qbm_b200.sample_qubo_batch(Q, 33, 200, seed=9, device=dev, return_energy=True, process_group=pg)
+        res["sa_energy"] = float(np.abs(s1.astype(int) - s2.astype(int)).max()) + float(np.abs(e1 - e2).max()) + \
+            (0.0 if e2.shape == (1, 33) else 1.0)
+        # the problem taken from rank 0 only (NCCL broadcast of Q): the other rank passes zeros of the right shape
+        Qr = Q if rank == 0 else np.zeros_like(Q)
+        s3, e3, _ = qbm_b200.sample_qubo_batch(Qr, 33, 200, seed=9, device=dev, return_energy=True, process_group=pg, src_rank=0)
+        res["sa_bcast"] = float(np.abs(s1.astype(int) - s3.astype(int)).max()) + float(np.abs(e1 - e3).max())
+        # seed=None: drawn on rank 0 and broadcast, so every rank returns the same (all) reads
+        s4, _, _ = qbm_b200.sample_qubo_batch(Q, 10, 50, seed=None, device=dev, return_energy=False, process_group=pg)
+        t4 = torch.from_numpy(s4.astype(np.int32)).to(dev)
+        t4max = t4.clone(); dist.all_reduce(t4max, op=dist.ReduceOp.MAX)
+        res["sa_seed"] = float((t4max - t4).abs().max())
+        # ---- ClassificationRBM CD-1, data-parallel: rank r draws from Philox stream step * world + r; the all-reduced update
+        # equals the sum of the two shard updates run separately (single-GPU steps with lr * B_local / B_global)
+        mk = lambda pg_: qbm_b200.B200ClassificationRBM(784, 500, 1, num_classes=10, learning_rate=0.05, seed=7, device=dev,
+                                                        process_group=pg_)
+        dp, alone = mk(pg), mk(None)
+        W0, U0, bv0 = dp.weights.clone(), dp.class_weights.clone(), dp.visible_bias.clone()
+        lo, hi = shard_range(64, world, rank)
+        dp.cd1_training(xb[lo:hi], yb[lo:hi], global_batch=64)
+        alone._step = rank                                   # stream = step * 1 + 0 = rank, the stream this rank used above
+        alone.learning_rate = 0.05 * (hi - lo) / 64.0
+        alone.cd1_training(xb[lo:hi], yb[lo:hi])
+        deltas = torch.cat([(alone.weights - W0).reshape(-1), (alone.class_weights - U0).reshape(-1),
+                            (alone.visible_bias - bv0).reshape(-1)])
+        dist.all_reduce(deltas, op=dist.ReduceOp.SUM)
+        got = torch.cat([(dp.weights - W0).reshape(-1), (dp.class_weights - U0).reshape(-1), (dp.visible_bias - bv0).reshape(-1)])
+        res["rbm_cd1"] = float((got - deltas).abs().max())
+        res["rbm_cd1_wt"] = float((dp._Wt[:, :784] - dp._W[:, :500].t()).abs().max())
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), res, allow_pickle=True)
     finally:
         dist.destroy_process_group()
@@ -98,6 +129,8 @@ def test_two_gpu_data_parallel_equals_single_gpu(tmp_path):
         res = np.load(tmp_path / f"rank{r}.npy", allow_pickle=True).item()
         assert res["disc"] < 1e-12, res          # float64 statistics: only the all-reduce summation order differs
         assert res["convdeep"] < 1e-9, res
+        assert res["sa_energy"] == 0.0 and res["sa_bcast"] == 0.0 and res["sa_seed"] == 0.0, res
+        assert res["rbm_cd1"] < 2e-5 and res["rbm_cd1_wt"] == 0.0, res
         assert res["rbm"] < 2e-5, res            # float32 parameters, TF32 products
         assert res["sa"] == 0.0, res             # bit-identical reads
         assert res["sa_gather"] == 0.0, res      # sharded + all-gathered sample_Q == single-GPU sample_Q
