@@ -271,6 +271,21 @@ class ConvDeepQBM:
         Ylab = Ylab.contiguous()
         Sc = self.sample_batch(self.build_qubos(fmap, pooled, Ylab, beta_eff), num_reads, first_image)
         Su = self.sample_batch(self.build_qubos(fmap, pooled, None, beta_eff), num_reads, first_image)
+        return self._step_from_samples(patches, Ylab, y, one_hot, Sc, Su, lr, global_batch)
+
+    def train_step_from_samples(self, X, Y, samples_clamped, samples_unclamped, lr: float, one_hot: bool = False,
+                                global_batch=None) -> float:
+        """The same step from given sample sets (int8 0/1 CUDA tensors [B, R, n_hidden] and [B, R, n_hidden + labels])
+        instead of the sampler's (the golden tests run the reference's recorded sample sets through the kernels)."""
+        fmap, pooled, patches = self.prepare_context_batch(X)
+        y, Ylab = self._labels(Y, fmap.shape[0], one_hot)
+        Sc, Su = samples_clamped.to(self.device).contiguous(), samples_unclamped.to(self.device).contiguous()
+        if Sc.dtype != torch.int8 or Su.dtype != torch.int8:
+            raise ValueError("sample sets must be int8 tensors")
+        return self._step_from_samples(patches, Ylab.contiguous(), y, one_hot, Sc, Su, lr, global_batch)
+
+    def _step_from_samples(self, patches, Ylab, y, one_hot, Sc, Su, lr, global_batch) -> float:
+        B = patches.shape[0]
         mc, sc = _s.phase_stats(Sc)
         mu, su = _s.phase_stats(Su)
         if self.keep_samples:

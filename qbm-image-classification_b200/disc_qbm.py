@@ -221,6 +221,23 @@ class DiscQBM:
         Y = self._labels(y_batch, B).contiguous()
         Sc = self.sample_batch(self.build_qubos(X, Y), first_image)
         Su = self.sample_batch(self.build_qubos(X, None), first_image)
+        return self._step_from_samples(X, Y, Sc, Su, learning_rate, global_batch)
+
+    def train_step_from_samples(self, x_batch, y_batch, samples_clamped, samples_unclamped, learning_rate, global_batch=None):
+        """The same step from given sample sets (int8 0/1 CUDA tensors [B, R, h] and [B, R, n_out + h]) instead of the
+        sampler's: statistics, errors, all-reduce and update as in ``train_for_one_iteration`` (what the golden tests use
+        to run the reference's recorded sample sets through the kernels)."""
+        X = self._to_dev(x_batch).contiguous()
+        B = X.shape[0]
+        Y = self._labels(y_batch, B).contiguous()
+        h, no = self.n_hidden_nodes, self.n_output_nodes
+        Sc, Su = samples_clamped.to(self.device).contiguous(), samples_unclamped.to(self.device).contiguous()
+        if Sc.dtype != torch.int8 or Su.dtype != torch.int8 or Sc.shape[::2] != (B, h) or Su.shape[::2] != (B, no + h):
+            raise ValueError("sample sets must be int8 tensors [B, R, h] (clamped) and [B, R, n_out + h] (unclamped)")
+        return self._step_from_samples(X, Y, Sc, Su, learning_rate, global_batch)
+
+    def _step_from_samples(self, X, Y, Sc, Su, learning_rate, global_batch):
+        B = X.shape[0]
         mean_c, sec_c = _s.phase_stats(Sc, second=not self.restricted and self.stats_mode == "loop")
         mean_u, sec_u = _s.phase_stats(Su, second=True)
         if self.keep_samples:

@@ -277,6 +277,91 @@ def recorded_accuracy_all(out):
     np.savez_compressed(out, **d)
 
 
+def disc_qbm_c5(out):
+    """discriminative_qbm.Disc_QBM at the C5 shapes (128 inputs, 10 one-hot labels, 512 hidden: n = 512 / 522), two images,
+    100 reads x 1000 sweeps.  Arrays too large to commit (QUBOs, W_vh, W_hh, their statistics) are stored as digests
+    (oracle.model_oracle.array_digest); sample sets and inputs in full."""
+    import src.model.discriminative_qbm as D
+    from oracle.model_oracle import array_digest as dg
+    from oracle.ref_stubs import _View
+    np.random.seed(77)                       # Appendix B Q12
+    m = D.Disc_QBM(dim_input=128, num_classes=10, use_one_hot_encoding=True, n_hidden_nodes=512, restricted=False,
+                   sample_count=100, anneal_steps=1000, beta_eff=1.0, parallelize=False, seed=77)
+    rng = np.random.default_rng(77)
+    X = rng.random((2, 128))
+    labels = np.array([7, 2])
+    Y = np.eye(10)[labels]
+    names = ["b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh"]
+    cur = lambda: dict(W_vh=m.weights_all_visible_to_hidden, W_vo=m.weights_clamped_visible_to_output,
+                       W_oo=m.weights_output_output, b_h=m.biases_hidden, b_o=m.biases_output, W_hh=m.weights_hidden_hidden)
+    d = dict(X=X, Y=Y, labels=labels, lr=0.1, seed=77, sample_count=100, anneal_steps=1000)
+    for k, v in cur().items():
+        d[f"w0_{k}_dg"] = dg(v)
+    d["w0_b_o"] = m.biases_output.copy(); d["w0_W_oo"] = m.weights_output_output.copy()
+    Sc, Su = [], []
+    for i in range(2):
+        d[f"Qc_dg_{i}"] = dg(m.create_qubo_matrix_from(X[i], Y[i]))
+        d[f"Qu_dg_{i}"] = dg(m.create_qubo_matrix_from(X[i]))
+        Sc.append(_samples_to_array(m.get_samples(X[i], label=Y[i])))
+        Su.append(_samples_to_array(m.get_samples(X[i])))
+        rc = m.get_average_configuration([_View(r) for r in Sc[i]], X[i], [Y[i]])
+        ru = m.get_average_configuration([_View(r) for r in Su[i]], X[i])
+        for nm, a, b in zip(names, rc, ru):
+            d[f"stat_c_{nm}_dg_{i}"] = dg(a); d[f"stat_u_{nm}_dg_{i}"] = dg(b)
+    d["Sc"] = np.stack(Sc); d["Su"] = np.stack(Su)
+    m.train_for_one_iteration(X, Y, 0.1, None)
+    for k, v in cur().items():
+        d[f"w1_{k}_dg"] = dg(v)
+    d["w1_b_o"] = m.biases_output.copy(); d["w1_W_oo"] = m.weights_output_output.copy()
+    np.savez_compressed(out, **d)
+
+
+def convdeep_c3(out):
+    """Conv_Deep_QBM at the C3 shapes (18x18 image, 3x3 kernel, pool 2 -> 64 pooled units, 128 sequential units, binary
+    label: n = 192 / 193) through src/train/train.py, two images, 1000 reads x 1000 sweeps; large arrays as digests."""
+    import src.model.cdqbm_state as C
+    import src.train.train as T
+    from src.train.pipeline import run_clamped, run_unclamped
+    from oracle.model_oracle import array_digest as dg
+    m = C.Conv_Deep_QBM(num_visible_nodes=324, num_lable_nodes=1, image_shape=(18, 18), kernel_size=3, pooling_size=2,
+                        pooling_type="deterministic", stride=1, sequential_layer_sizes=[128], is_restricted=False,
+                        hidden_bias_type="shared", solver="SA", anneal=1000, seed=44)
+    rng = np.random.default_rng(19)
+    X = rng.random((2, 18, 18)).astype(np.float32)
+    Y = np.array([1, 0])
+    num_reads, lr = 1000, 0.01
+    cur = lambda: dict(kernel=m.kernel_weights, W_seq0=m.weights_sequential_layer[0], W_hy=m.weights_hidden_to_output,
+                       W_oo=m.weights_output_output, W_intra0=m.weights_interlayer_sequential[0], b_conv=m.biases_conv_units,
+                       b_seq=m.biases_sequential_units, b_out=m.biases_output)
+    d = dict(X=X, Y=Y, lr=lr, num_reads=num_reads, anneal=1000, seed=44)
+    for k, v in cur().items():
+        d[f"w0_{k}_dg"] = dg(v)
+    d["w0_kernel"] = m.kernel_weights.copy()
+    rec = _Recorder(m.sampler)
+    m.sampler = rec
+    names = ["b_conv", "b_seq", "b_out", "kernel", "W_intra", "W_seq", "W_hy", "W_oo"]
+    probs = []
+    for i in range(2):
+        lab = np.array([float(Y[i])])
+        oc = run_clamped(m, X[i], lab, num_reads, 1.0)
+        ou = run_unclamped(m, X[i], num_reads, 1.0, False)
+        probs.append(ou.probs)
+        for tag, o, yy in (("c", oc, lab), ("u", ou, None)):
+            r = T.get_average_configuration_single(m, o, X[i], y=yy)
+            for nm, a in zip(names, r):
+                a = a[0] if isinstance(a, list) else a
+                d[f"stat_{tag}_{nm}_dg_{i}"] = dg(a)
+    for i in range(2):
+        d[f"Qc_dg_{i}"] = dg(rec.Q[2 * i]); d[f"Qu_dg_{i}"] = dg(rec.Q[2 * i + 1])
+    d["Sc"] = np.stack(rec.S[0:4:2]).astype(np.int8); d["Su"] = np.stack(rec.S[1:4:2]).astype(np.int8)
+    d["probs"] = np.stack(probs)
+    d["loss"] = T.train_one_iteration(m, X, Y, num_reads, 1.0, lr, one_hot=False)
+    for k, v in cur().items():
+        d[f"w1_{k}_dg"] = dg(v)
+    d["w1_kernel"] = m.kernel_weights.copy()
+    np.savez_compressed(out, **d)
+
+
 def main():
     with ref_stubs.reference_imports():
         disc_qbm_loop(os.path.join(HERE, "disc_qbm_loop_onehot.npz"))
@@ -286,6 +371,8 @@ def main():
         rbm(os.path.join(HERE, "rbm_discriminative.npz"))
         recorded_accuracy(os.path.join(HERE, "pneumonia_h10_recorded_accuracy.npz"))
         recorded_accuracy_all(os.path.join(HERE, "pneumonia_last_epoch_recorded_accuracy.npz"))
+        disc_qbm_c5(os.path.join(HERE, "disc_qbm_loop_c5.npz"))
+        convdeep_c3(os.path.join(HERE, "convdeep_c3.npz"))
     for f in sorted(glob.glob(os.path.join(HERE, "*.npz"))):
         print(f"{os.path.basename(f):45s} {os.path.getsize(f) / 1024:8.1f} KB")
 

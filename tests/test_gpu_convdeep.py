@@ -78,6 +78,48 @@ def test_convdeep_training_step(qbm, cuda, name, one_hot):
     assert probs.shape == (3, 3 if one_hot else 2) and np.allclose(probs.sum(axis=1), 1.0, atol=1e-6)
 
 
+def test_convdeep_training_step_at_the_c3_shapes(qbm, cuda):
+    """C3 (BASELINE config 3: 18x18 image, 3x3 kernel, pool 2 -> 64 pooled units, 128 sequential units, 1000 reads x 1000
+    sweeps; n = 192 / 193) against the golden generated from Conv_Deep_QBM through src/train: initial draws and both QUBO
+    builders equal the reference's (digests), the reference's own sample sets through K3 + K11 + K9 give its parameters and
+    loss after one step, and a whole step on the GPU's samples equals the reference arithmetic on those samples."""
+    g = np.load(os.path.join(G, "convdeep_c3.npz"))
+    m = qbm.ConvDeepQBM(num_visible_nodes=324, num_lable_nodes=1, image_shape=(18, 18), kernel_size=3, pooling_size=2,
+                        pooling_type="deterministic", stride=1, sequential_layer_sizes=[128], is_restricted=False,
+                        hidden_bias_type="shared", solver="SA", anneal=int(g["anneal"]), seed=int(g["seed"]))
+    flat = lambda p: dict(kernel=p["kernel"], W_seq0=p["W_seq"][0], W_hy=p["W_hy"], W_oo=p["W_oo"], W_intra0=p["W_intra"][0],
+                          b_conv=p["b_conv"], b_seq=p["b_seq"], b_out=p["b_out"])
+    p0 = m.get_params()
+    for k, v in flat(p0).items():
+        assert np.allclose(M.array_digest(v), g[f"w0_{k}_dg"], rtol=1e-10, atol=1e-9), f"initial {k}"
+    X, Y = g["X"], g["Y"]
+    fmap, pooled, patches = m.prepare_context_batch(X)
+    assert m.num_pooled_units == 64 and m.n_hidden == 192
+    lab = torch.from_numpy(Y.astype(np.float64)[:, None]).to(cuda)
+    Qc, Qu = m.build_qubos(fmap, pooled, lab).cpu().numpy(), m.build_qubos(fmap, pooled, None).cpu().numpy()
+    for i in range(2):
+        assert np.allclose(M.array_digest(Qc[i]), g[f"Qc_dg_{i}"], rtol=1e-10, atol=1e-9)
+        assert np.allclose(M.array_digest(Qu[i]), g[f"Qu_dg_{i}"], rtol=1e-10, atol=1e-9)
+    R, lr = int(g["num_reads"]), float(g["lr"])
+    loss = m.train_step_from_samples(X, Y, torch.from_numpy(g["Sc"]).to(cuda), torch.from_numpy(g["Su"]).to(cuda), lr)
+    assert abs(loss - float(g["loss"])) < 1e-6
+    for k, v in flat(m.get_params()).items():
+        assert np.allclose(M.array_digest(v), g[f"w1_{k}_dg"], rtol=1e-6, atol=1e-6), f"after one step: {k}"
+    p1 = m.get_params()
+    m.keep_samples = True
+    loss = m.train_one_iteration(X, Y, R, 1.0, lr)
+    Sc, Su = (t.cpu().numpy().astype(np.float32) for t in m.last_samples)
+    assert Sc.shape == (2, 1000, 192) and Su.shape == (2, 1000, 193)
+    ref, ref_loss = M.convdeep_train_step(p1, X, Y, Sc, Su, lr, 1, 2, False)
+    assert abs(loss - ref_loss) < 1e-6
+    got = m.get_params()
+    for k, v in ref.items():
+        a, b = (got[k][0], v[0]) if isinstance(v, list) else (got[k], v)
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-7), k
+    probs = m.predict_proba_batch(X, R, 1.0, False)
+    assert probs.shape == (2, 2) and np.allclose(probs.sum(axis=1), 1.0, atol=1e-6)
+
+
 def test_convdeep_restricted_no_bias_and_float64_stats(qbm, cuda):
     """is_restricted=True (no within-layer couplings), hidden_bias_type='none', two sequential layers."""
     rng = np.random.default_rng(11)

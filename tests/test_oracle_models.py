@@ -121,6 +121,71 @@ def test_recorded_accuracy_by_exact_enumeration():
         assert abs(roc_auc_score(labels, pred) - float(g[f"auc_{k}"])) < 1e-12
 
 
+def _dg_close(a, ref, tag):
+    assert np.allclose(M.array_digest(a), ref, rtol=1e-10, atol=1e-9), tag
+
+
+def test_disc_qbm_at_the_c5_shapes_matches_reference():
+    """Golden from discriminative_qbm.Disc_QBM at C5 (128 inputs, 10 one-hot labels, 512 hidden: n = 512 / 522), two images,
+    100 reads x 1000 sweeps: initial draws, both QUBO builders, the loop statistics of both phases and the parameters after
+    one training step of the reference equal the oracle's (large arrays compared through their digests)."""
+    g = load("disc_qbm_loop_c5.npz")
+    np.random.seed(77)                                           # Appendix B Q12
+    p0 = M.disc_init_params(128, 10, 512, int(g["seed"]))
+    for k, v in p0.items():
+        _dg_close(v, g[f"w0_{k}_dg"], f"initial {k}")
+    assert np.array_equal(p0["b_o"], g["w0_b_o"]) and np.array_equal(p0["W_oo"], g["w0_W_oo"])
+    X, Y, Sc, Su = g["X"], g["Y"], g["Sc"], g["Su"]
+    assert Sc.shape == (2, 100, 512) and Su.shape == (2, 100, 522)
+    names = ["b_h", "b_o", "W_vh", "W_vo", "W_oo", "W_hh"]
+    for i in range(2):
+        _dg_close(M.disc_qubo(p0, X[i], Y[i]), g[f"Qc_dg_{i}"], f"Qc {i}")
+        _dg_close(M.disc_qubo(p0, X[i]), g[f"Qu_dg_{i}"], f"Qu {i}")
+        rc = M.disc_stats_loop(Sc[i], X[i], Y[i], 10, 128, 512)
+        ru = M.disc_stats_loop(Su[i], X[i], None, 10, 128, 512)
+        for nm, a, b in zip(names, rc, ru):
+            _dg_close(a, g[f"stat_c_{nm}_dg_{i}"], f"clamped {nm} {i}")
+            _dg_close(b, g[f"stat_u_{nm}_dg_{i}"], f"unclamped {nm} {i}")
+    new = M.disc_train_step(p0, X, Y, Sc, Su, float(g["lr"]), "loop")
+    for k, v in new.items():
+        _dg_close(v, g[f"w1_{k}_dg"], f"after one step: {k}")
+    assert np.allclose(new["b_o"], g["w1_b_o"], rtol=0, atol=1e-13) and np.allclose(new["W_oo"], g["w1_W_oo"], rtol=0, atol=1e-13)
+
+
+def test_convdeep_at_the_c3_shapes_matches_reference():
+    """Golden from Conv_Deep_QBM through src/train at C3 (18x18, 3x3 kernel, pool 2 -> 64 pooled, 128 sequential units, binary
+    label: n = 192 / 193), two images, 1000 reads x 1000 sweeps."""
+    g = load("convdeep_c3.npz")
+    p0 = M.convdeep_init_params(64, [128], 1, 3, int(g["seed"]))
+    flat = dict(kernel=p0["kernel"], W_seq0=p0["W_seq"][0], W_hy=p0["W_hy"], W_oo=p0["W_oo"], W_intra0=p0["W_intra"][0],
+                b_conv=p0["b_conv"], b_seq=p0["b_seq"], b_out=p0["b_out"])
+    for k, v in flat.items():
+        _dg_close(v, g[f"w0_{k}_dg"], f"initial {k}")
+    assert np.array_equal(p0["kernel"], g["w0_kernel"])
+    X, Y, Sc, Su = g["X"], g["Y"], g["Sc"], g["Su"]
+    assert Sc.shape == (2, 1000, 192) and Su.shape == (2, 1000, 193)
+    names = ["b_conv", "b_seq", "b_out", "kernel", "W_intra", "W_seq", "W_hy", "W_oo"]
+    for i in range(2):
+        f, pooled, patches = M.convdeep_context(X[i], p0["kernel"], 1, 2)
+        assert len(pooled) == 64
+        lab = np.array([float(Y[i])])
+        _dg_close(M.convdeep_qubo(p0, f, pooled, lab), g[f"Qc_dg_{i}"], f"Qc {i}")
+        _dg_close(M.convdeep_qubo(p0, f, pooled, None), g[f"Qu_dg_{i}"], f"Qu {i}")
+        for tag, S, yy in (("c", Sc[i], lab), ("u", Su[i], None)):
+            r = M.convdeep_stats(S.astype(np.float32), X[i], yy, 64, [128], 1, patches)
+            for nm, a in zip(names, r):
+                a = a[0] if isinstance(a, list) else a
+                assert np.allclose(M.array_digest(a), g[f"stat_{tag}_{nm}_dg_{i}"], rtol=1e-9, atol=1e-9), (tag, nm, i)
+        assert np.allclose(M.convdeep_probs(Su[i].astype(np.float32), 192, False), g["probs"][i], rtol=1e-6)
+    new, loss = M.convdeep_train_step(p0, X, Y, Sc.astype(np.float32), Su.astype(np.float32), float(g["lr"]), 1, 2, False)
+    assert abs(loss - float(g["loss"])) < 1e-9
+    flat1 = dict(kernel=new["kernel"], W_seq0=new["W_seq"][0], W_hy=new["W_hy"], W_oo=new["W_oo"], W_intra0=new["W_intra"][0],
+                 b_conv=new["b_conv"], b_seq=new["b_seq"], b_out=new["b_out"])
+    for k, v in flat1.items():
+        assert np.allclose(M.array_digest(v), g[f"w1_{k}_dg"], rtol=1e-9, atol=1e-9), f"after one step: {k}"
+    assert np.allclose(new["kernel"], g["w1_kernel"], rtol=1e-9, atol=1e-12)
+
+
 def _majority_predictions_of_run(args):
     """Worker (forked process): Disc_QBM.predict for every test image of one recorded run through oracle.neal_sample."""
     from oracle import oracle as O
