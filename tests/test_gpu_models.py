@@ -332,6 +332,44 @@ def test_disc_qbm_training_accuracy_within_1pp_of_cpu_reference_loop(qbm, oracle
     assert abs(acc_gpu - acc_cpu) <= 0.01 + 1e-9, (acc_gpu, acc_cpu)
 
 
+def test_disc_qbm_accuracy_at_the_c1_shape_within_1pp_of_cpu_reference_loop(qbm, oracle, cuda):
+    """Criterion 4 at the C1 shape (BASELINE config 1: 16 inputs, 10 one-hot labels, 24 hidden units, 100 reads x 1000 sweeps,
+    minibatch 73; QUBO n = 24 / 34) on SURVEY.md 8d's synthetic 28x28 images: 10 epochs over 292 images through the batched
+    GPU step and through the reference's per-image loop restated on the CPU (same initial draws, same minibatches, the
+    restated neal as sampler), then accuracy on 1000 test images.  The 16 inputs are a fixed linear projection of the
+    flattened image (the 10 class templates as matched filters + 6 random directions), rescaled to [0, 1], so that the task
+    is learnable to > 90 % and the comparison is not dominated by noise; |accuracy difference| <= 1 pp."""
+    from concurrent.futures import ThreadPoolExecutor
+    import bench_train as BT
+    ntr, nte, reads, sweeps, lr, seed = 292, 1000, 100, 1000, 1.5, 19
+    x, y = BT.synthetic_images(ntr + nte, (28, 28), 10, seed)
+    templates = np.random.default_rng(seed).random((10, 784)) < 0.5             # the generator's own templates
+    P = np.concatenate([(templates - 0.5), np.random.default_rng(seed + 1).standard_normal((6, 784))]) / 28.0
+    z = x.reshape(len(x), -1).astype(np.float64) @ P.T
+    X = (z - z.min(axis=0)) / (z.max(axis=0) - z.min(axis=0))
+    Yoh = np.eye(10)[y]
+    Xtr, Ytr, Xte, yte = X[:ntr], Yoh[:ntr], X[ntr:], y[ntr:]
+    np.random.seed(seed)
+    m = qbm.DiscQBM(dim_input=16, num_classes=10, use_one_hot_encoding=True, n_hidden_nodes=24, restricted=False,
+                    sample_count=reads, anneal_steps=sweeps, beta_eff=1.0, seed=seed, stats_mode="loop")
+    p = m.get_params()
+    pool = ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, 16))
+    sample = lambda Q: oracle.sample_Q_reference(Q, reads, sweeps, seed=seed)
+    for _ in range(10):
+        for s in range(0, ntr, 73):
+            xb, yb = Xtr[s:s + 73], Ytr[s:s + 73]
+            m.train_for_one_iteration(xb, yb, lr)
+            Sc = list(pool.map(sample, [M.disc_qubo(p, a, b) for a, b in zip(xb, yb)]))
+            Su = list(pool.map(sample, [M.disc_qubo(p, a, None) for a in xb]))
+            p = M.disc_train_step(p, xb, yb, Sc, Su, lr, "loop")
+    acc_gpu = float(np.mean(m.predict_batch(Xte) == yte))
+    Ste = list(pool.map(sample, [M.disc_qubo(p, a, None) for a in Xte]))
+    acc_cpu = float(np.mean(np.array([M.disc_predict(S, 10, True) for S in Ste]) == yte))
+    pool.shutdown()
+    assert acc_cpu > 0.9 and acc_gpu > 0.9, (acc_gpu, acc_cpu)
+    assert abs(acc_gpu - acc_cpu) <= 0.01 + 1e-9, (acc_gpu, acc_cpu)
+
+
 def test_epoch_loops_and_checkpoints(qbm, cuda, tmp_path):
     """L4 callers of the path: Disc_QBM.train_model (faster_dqbm.py:1079-1166) with per-epoch weight pickles in the
     reference's format, load_savepoint (:169-190), and train.py::train_model for the Conv-Deep model."""

@@ -124,6 +124,37 @@ def test_rbm_training_accuracy_within_1pp_of_cpu_reference_math(qbm, cuda):
     assert np.allclose(m.weights.cpu().numpy(), W, atol=5e-4)
 
 
+def test_rbm_epochs_accuracy_within_1pp_discriminative_and_cd1(qbm, cuda):
+    """north_star criterion 4 at the C2 shapes (784 + 10 visible, 500 hidden, batch 256) over training RUNS, not single
+    steps: 3 epochs over 2560 synthetic images (30 steps) in each training mode, then test accuracy on 2000 images.
+      discriminative  (ClassificationRBM.py:101-146): the GPU run against the same steps in the float32 numpy oracle
+      CD-1            (the composition of :43-60): the GPU run against the float64 replay oracle fed the kernel's
+                      own Philox streams step by step
+    Both arms start from the same initial draws and see the same minibatches; |accuracy difference| <= 1 pp."""
+    V, H, C, B, steps = 784, 500, 10, 256, 30
+    xtr, ytr = synthetic_images(2560, 1)
+    xte, yte = synthetic_images(2000, 2)
+    for mode, lr in (("discriminative", 0.05), ("cd1", 0.05)):
+        m = qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=lr, seed=42)
+        W, U = m.weights.cpu().numpy().astype(np.float64), m.class_weights.cpu().numpy().astype(np.float64)
+        bv, bh, bc = (t.cpu().numpy().astype(np.float64) for t in (m.visible_bias, m.hidden_bias, m.class_bias))
+        for s in range(steps):
+            i = (s % 10) * B
+            xb, yb = xtr[i:i + B], ytr[i:i + B]
+            if mode == "discriminative":
+                m.discriminative_training(torch.from_numpy(xb), torch.from_numpy(yb))
+                new, *_ = M.rbm_discriminative_step(W.astype(np.float32), U.astype(np.float32), bv.astype(np.float32),
+                                                    bh.astype(np.float32), bc.astype(np.float32), xb, yb, np.float32(lr))
+            else:
+                m.cd1_training(torch.from_numpy(xb), torch.from_numpy(yb))
+                new, _ = M.rbm_cd1_step_replay(W, U, bv, bh, bc, xb, yb, lr, 42, s)
+            W, U, bv, bh, bc = (np.asarray(new[k], dtype=np.float64) for k in ("W", "U", "b_v", "b_h", "b_c"))
+        acc_gpu = float((m.predict(torch.from_numpy(xte)).cpu().numpy() == yte).mean())
+        acc_ref = float((M.rbm_class_given_x(W, U, bh, bc, xte.astype(np.float64)).argmax(axis=1) == yte).mean())
+        assert acc_ref > 0.5, (mode, acc_ref)                       # the synthetic task is learnable in this mode
+        assert abs(acc_gpu - acc_ref) <= 0.01 + 1e-9, (mode, acc_gpu, acc_ref)
+
+
 def test_rbm_cd1_step_statistics(qbm, cuda):
     """CD-1 composition: the update equals lr/B * (v0^T ph0 - v1^T ph1) for SOME valid Bernoulli draws: check
     the deterministic parts exactly (positive phase) and the sampled parts statistically."""
