@@ -8,7 +8,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqbm_b200.so")
+# QBM_B200_LIB: an instrumented build of the same library (tools/probe_tile_prof.py); there is still no fallback
+LIB_PATH = os.environ.get("QBM_B200_LIB") or os.path.join(HERE, "libqbm_b200.so")
 
 QBM_OK = 0
 QBM_EINVAL = -1

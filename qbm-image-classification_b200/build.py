@@ -36,9 +36,16 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in files)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, variant: str = "", extra: tuple = ()) -> str:
+    """`variant` / `extra`: an instrumented build (own object directory and library name, extra nvcc flags)."""
+    if variant:
+        return _build(True, verbose, os.path.join(HERE, "build_" + variant), os.path.join(HERE, f"libqbm_b200_{variant}.so"), tuple(extra))
     if not force and not needs_build():
         return LIB
+    return _build(force, verbose, OBJ, LIB, ())
+
+
+def _build(force, verbose, OBJ, LIB, extra) -> str:
     nvcc = os.environ.get("NVCC", "nvcc")
     os.makedirs(OBJ, exist_ok=True)
     hdr_t = max(os.path.getmtime(f) for f in _deps() + [__file__])
@@ -48,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         s = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(s), hdr_t):
             return obj
-        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("QBM_NVCC_EXTRA", "").split(), "-c", s, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *os.environ.get("QBM_NVCC_EXTRA", "").split(), "-c", s, "-o", obj]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -13,11 +13,14 @@
 //             RECORDS in order: for every flipped variable a of a record (sweep order) the row J[a] is read once from
 //             the ring and applied to all chains that flipped a: F[.][t] = fma(c_t, J[a][.], F[.][t]) (FFMA2).  Before
 //             applying record r the owner of sub-window r+1 exports that sub-window's 32 x 16 fields to shared memory.
-//   scanner   warp 9, lane = chain x half: takes the exported fields of sub-window r+1 (they contain every flip up to
-//             record r-1), applies record r to them itself from the 32x32 block J[rows of r][columns of r+1] -- the same
-//             FMAs in the same order as the appliers will -- then visits the 32 variables in sweep order (a flip
-//             updates the 32 fields from the diagonal block) and publishes record r+1: per chain a flip mask, the old
-//             spins and a coefficient matrix c[a][t] in {0, +-2}.  Spins live with the scanner only.
+//   scanners  warps 9 and 11, TS = 8 chains each, lane = chain x part (a part = 8 variables of the sub-window): take the
+//             exported fields of sub-window r+1 (they contain every flip up to record r-1), apply record r to them
+//             themselves from the 32x32 block J[rows of r][columns of r+1] -- the same FMAs in the same order as the
+//             appliers will -- then visit the 32 variables in sweep order (a flip updates the 32 fields from the
+//             diagonal block) and publish their half of record r+1: per chain a flip mask, the old spins and a
+//             coefficient matrix c[a][t] in {0, +-2}.  Spins live with the scanners only.  The scan is a chain of
+//             dependent instructions (one warp retires one every ~5 clocks); the chains of a tile are independent, so
+//             two warps on two schedulers halve the time per sub-window, which is what bounds the kernel.
 //   bounds    warp 10: Philox + -ln(u)/beta acceptance bounds of the next 128-variable window, double-buffered
 //   producer  warp 8, one lane: one cp.async.bulk (TMA, 1-D) per flipped coupling row into a ring of 16 rows, one
 //             mbarrier full/empty hand-shake per ring slot of 4 rows; rows come from L2 (the matrix is read once per
@@ -36,14 +39,41 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+
+// -DQBM_TILE_PROF: clocks the warp roles spend waiting on each hand-off (tools/probe_tile_prof.py); never in the shipped build
+#ifdef QBM_TILE_PROF
+__device__ unsigned long long g_tile_prof[32];
+#define PROF_VAR(x) uint32_t x = 0u
+#define PROF_WAIT(x, stmt) do { const uint32_t _t0 = (uint32_t)clock(); stmt; x += (uint32_t)clock() - _t0; } while (0)
+#define PROF_PUT(i, x) atomicAdd(&g_tile_prof[i], (unsigned long long)(x))
+#else
+#define PROF_VAR(x)
+#define PROF_WAIT(x, stmt) do { stmt; } while (0)
+#define PROF_PUT(i, x)
+#endif
 constexpr int T = 16;             // chains per CTA
-constexpr int GR = 4;             // coupling rows per ring slot: one full / empty hand-shake per GR rows
-constexpr int NGS = 4;            // ring slots
+#ifndef QBM_TILE_GR
+#define QBM_TILE_GR 4
+#define QBM_TILE_NGS 4
+#endif
+constexpr int GR = QBM_TILE_GR;   // coupling rows per ring slot: one full / empty hand-shake per GR rows
+constexpr int NGS = QBM_TILE_NGS; // ring slots (a power of two)
 constexpr int RB = GR * NGS;      // coupling rows in flight per CTA
 constexpr int NREC = 4;           // record buffers (the scanner runs at most one sub-window ahead of the slowest applier)
 constexpr int FXLD = 32 * T + 32; // floats per field-export buffer: [column][chain], the upper 16 columns shifted by 16
 constexpr int NTHREADS = 384;
-constexpr int WARP_PRODUCER = 8, WARP_SCANNER = 9, WARP_BOUNDS = 10;
+constexpr int WARP_PRODUCER = 8, WARP_BOUNDS = 10;
+constexpr int NSCAN = 2;          // scanner warps (warps 9 and 11: one per scheduler that holds no other helper warp)
+constexpr int TS = T / NSCAN;     // chains per scanner warp; lane = chain (TS) x part (32 / TS), a part = TS variables
+constexpr int NPART = 32 / TS;
+static_assert(NSCAN == 1 || NSCAN == 2, "rowmask words are written as 32 / NSCAN-bit halves");
+__device__ __forceinline__ int scanner_of_warp(int warp) { return warp == 9 ? 0 : (NSCAN == 2 && warp == 11 ? 1 : -1); }
+// a rowmask word holds, per scanner, TS flip bits then TS old-spin bits: chain t flipped <=> bit flip_bit(t), its old spin
+// is bit flip_bit(t) + TS
+__host__ __device__ constexpr int flip_bit(int t) { return (t / TS) * 2 * TS + (t % TS); }
+// record meta words
+constexpr int META = 8, M_UNION = 0, M_COUNT = 2, M_ROW0 = 4, M_EXIT = 5;
+constexpr uint32_t DENSE_MARK = 0x0fffffffu;
 constexpr int REGS_APPLIER = 208, REGS_HELPER = 88;      // 2 * 208 + 88 = 504 = 3 * 168 (the launch allocation)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,14 +177,14 @@ __device__ __forceinline__ void tile_sync(int nthreads) { asm volatile("bar.sync
 
 struct TileSmem {
     float *ring;         // [RB][ld]
-    float *Dbuf;         // [2][64][32]  rows 0..31: J[rows of the previous sub-window][columns of this one], 32..63: diagonal block
+    float *Dbuf;         // [NSCAN][2][64][32]  rows 0..31: J[rows of the previous sub-window][columns of this one], 32..63: diagonal block
     float *Fx;           // [2][FXLD]    exported fields of the sub-window the scanner visits next
     float *bounds;       // [2][4][32][T] acceptance bounds of a 128-variable window
-    float *Cbuf;         // [NREC][32][T][2] update coefficients of a record, each stored twice: (c, c) is an FFMA2 operand
+    float *Cbuf;         // [NREC][32][T]   update coefficients of a record (the FFMA2 takes them as a broadcast scalar operand)
     uint32_t *spinw;     // [MAXSUB][T]  spins, one word per (sub-window, chain)
-    uint32_t *rowmask;   // [NREC][32]   per flipped variable: chains that flipped it (bits 0..15), their old spins (bits 16..31)
-    uint32_t *rec_meta;  // [NREC][4]    union of the flip masks, number of flips, first row, exit flag
-    uint32_t *ctl;       // [4]          [0] exit flag for the bounds warp
+    uint32_t *rowmask;   // [NREC][32]   per flipped variable: chains that flipped it and their old spins (flip_bit)
+    uint32_t *rec_meta;  // [NREC][META] per scanner: union of the flip masks, number of flips; first row, exit flag
+    uint32_t *ctl;       // [12]         [0] exit flag for the bounds warp, [1..] flips of a sweep per scanner (two parities)
     uint64_t *full;      // [NGS]  ring slot filled (producer -> appliers)
     uint64_t *empty;     // [NGS]  ring slot released (appliers -> producer)
     uint64_t *rec_full;  // [NREC] record published (scanner -> appliers, producer)
@@ -169,14 +199,14 @@ struct TileSmem {
 // the only part whose size depends on n -- last; all shared addresses of the control path fold to base + immediate
 constexpr int MAXSUB = QBM_SA_MAX_N / 32;             // sub-windows of the largest problem
 constexpr size_t OFF_DBUF = 0;
-constexpr size_t OFF_FX = OFF_DBUF + 2 * 64 * 32 * 4;
+constexpr size_t OFF_FX = OFF_DBUF + (size_t)NSCAN * 2 * 64 * 32 * 4;
 constexpr size_t OFF_BOUNDS = OFF_FX + 2 * FXLD * 4;
 constexpr size_t OFF_CBUF = OFF_BOUNDS + 2 * 4 * 32 * T * 4;
-constexpr size_t OFF_SPINW = OFF_CBUF + NREC * 32 * T * 8;
+constexpr size_t OFF_SPINW = OFF_CBUF + NREC * 32 * T * 4;
 constexpr size_t OFF_ROWMASK = OFF_SPINW + (size_t)MAXSUB * T * 4;
 constexpr size_t OFF_META = OFF_ROWMASK + NREC * 32 * 4;
-constexpr size_t OFF_CTL = OFF_META + NREC * 4 * 4;
-constexpr size_t OFF_BARS = OFF_CTL + 4 * 4;
+constexpr size_t OFF_CTL = OFF_META + NREC * META * 4;
+constexpr size_t OFF_BARS = OFF_CTL + 12 * 4;
 constexpr size_t OFF_RING = (OFF_BARS + (size_t)(2 * NGS + 2 * NREC + 8) * 8 + 127) / 128 * 128;
 
 __host__ __device__ inline size_t tile_smem_bytes(int ld) { return OFF_RING + (size_t)RB * ld * 4; }
@@ -230,18 +260,22 @@ __device__ __forceinline__ void row_load(RowRegs<NS> &R, const TileAddr &A, uint
 template <int NS>
 __device__ __forceinline__ void row_apply_dense(f32x2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
-    // coefficients come as ready (c, c) pairs, two chains per 128-bit load (warp-uniform address: a broadcast)
+    // four chains per 128-bit load (warp-uniform address: a broadcast); (c, c) is a scalar operand of the FFMA2
 #pragma unroll
-    for (int t2 = 0; t2 < T / 2; ++t2) {
-        const float4 c4 = lds128(R.c + (uint32_t)t2 * 16u);
-        const f32x2 ca = pack2(c4.x, c4.y), cb = pack2(c4.z, c4.w);
+    for (int t4 = 0; t4 < T / 4; ++t4) {
+        const float4 c4 = lds128(R.c + (uint32_t)t4 * 16u);
+        const f32x2 c0 = pack2(c4.x, c4.x), c1 = pack2(c4.y, c4.y), c2 = pack2(c4.z, c4.z), c3 = pack2(c4.w, c4.w);
 #pragma unroll
         for (int jw = 0; jw < NS / 4; ++jw) {
             const f32x2 r01 = pack2(R.r[jw].x, R.r[jw].y), r23 = pack2(R.r[jw].z, R.r[jw].w);
-            ffma2(F2[jw * 2 + 0][2 * t2], ca, r01);
-            ffma2(F2[jw * 2 + 1][2 * t2], ca, r23);
-            ffma2(F2[jw * 2 + 0][2 * t2 + 1], cb, r01);
-            ffma2(F2[jw * 2 + 1][2 * t2 + 1], cb, r23);
+            ffma2(F2[jw * 2 + 0][4 * t4 + 0], c0, r01);
+            ffma2(F2[jw * 2 + 1][4 * t4 + 0], c0, r23);
+            ffma2(F2[jw * 2 + 0][4 * t4 + 1], c1, r01);
+            ffma2(F2[jw * 2 + 1][4 * t4 + 1], c1, r23);
+            ffma2(F2[jw * 2 + 0][4 * t4 + 2], c2, r01);
+            ffma2(F2[jw * 2 + 1][4 * t4 + 2], c2, r23);
+            ffma2(F2[jw * 2 + 0][4 * t4 + 3], c3, r01);
+            ffma2(F2[jw * 2 + 1][4 * t4 + 3], c3, r23);
         }
     }
 }
@@ -249,11 +283,11 @@ __device__ __forceinline__ void row_apply_dense(f32x2 (&F2)[NS / 2][T], const Ro
 template <int NS>
 __device__ __forceinline__ void row_apply_sparse(f32x2 (&F2)[NS / 2][T], const RowRegs<NS> &R)
 {
-    const uint32_t m = R.c;              // bits 0..15: chains that flipped this variable, bits 16..31: their old spins
+    const uint32_t m = R.c;              // the row's mask word: chains that flipped this variable and their old spins
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        if ((m >> t) & 1u) {             // warp-uniform
-            const float c = ((m >> (16 + t)) & 1u) ? -2.0f : 2.0f;
+        if ((m >> flip_bit(t)) & 1u) {   // warp-uniform
+            const float c = ((m >> (flip_bit(t) + TS)) & 1u) ? -2.0f : 2.0f;
             const f32x2 cc = pack2(c, c);
 #pragma unroll
             for (int jw = 0; jw < NS / 4; ++jw) {
@@ -269,9 +303,9 @@ __device__ __forceinline__ void row_apply_sparse(f32x2 (&F2)[NS / 2][T], const R
 // rows of a group at static offsets -- the per-row bookkeeping is the next set bit of `u` and two address adds.
 template <int NS>
 __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileAddr &A, uint32_t u, uint32_t count, uint32_t rb,
-                                             int lane, uint32_t &gi, uint32_t dense_min)
+                                             int lane, uint32_t &gi, uint32_t dense_min, uint32_t &w_ring)
 {
-    const uint32_t cb_rec = A.cbuf + rb * (32u * T * 8u);
+    const uint32_t cb_rec = A.cbuf + rb * (32u * T * 4u);
     const uint32_t rm_rec = A.rowmask + rb * (32u * 4u);
     // The dense and the sparse loop are kept apart: one loop with both bodies makes ptxas reconcile the 128 field
     // registers with moves
@@ -281,7 +315,7 @@ __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileA
             const uint32_t slot = gi & (NGS - 1);
             const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
             const uint32_t base = A.ring + slot * (GR * A.slot_stride);
-            mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
+            PROF_WAIT(w_ring, mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u));
             if (cnt == (uint32_t)GR) {
                 // a full group (nearly all of them while the sweeps are hot): four rows, straight-line
 #pragma unroll
@@ -290,7 +324,7 @@ __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileA
                     u &= u - 1;
                     RowRegs<NS> R;
                     row_load<NS>(R, A, base + j * A.slot_stride);
-                    R.c = cb_rec + (uint32_t)a * (T * 8u);
+                    R.c = cb_rec + (uint32_t)a * (T * 4u);
                     row_apply_dense<NS>(F2, R);
                 }
             } else {
@@ -300,7 +334,7 @@ __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileA
                     u &= u - 1;
                     RowRegs<NS> R;
                     row_load<NS>(R, A, base + j * A.slot_stride);
-                    R.c = cb_rec + (uint32_t)a * (T * 8u);
+                    R.c = cb_rec + (uint32_t)a * (T * 4u);
                     row_apply_dense<NS>(F2, R);
                 }
             }
@@ -314,7 +348,7 @@ __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileA
             const uint32_t slot = gi & (NGS - 1);
             const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
             const uint32_t base = A.ring + slot * (GR * A.slot_stride);
-            mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u);
+            PROF_WAIT(w_ring, mbar_wait_s(A.full + slot * 8u, (gi / NGS) & 1u));
 #pragma unroll 1
             for (uint32_t j = 0; j < cnt; ++j) {
                 const int a = __ffs(u) - 1;
@@ -335,19 +369,24 @@ __device__ __forceinline__ void apply_record(f32x2 (&F2)[NS / 2][T], const TileA
 __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *__restrict__ Jp, int ld)
 {
     uint32_t r = 0, ri = 0;
+    PROF_VAR(w_rec); PROF_VAR(w_empty);
+#ifdef QBM_TILE_PROF
+    const uint32_t t_start = (uint32_t)clock();
+#endif
     while (true) {
         const uint32_t rb = r & (NREC - 1);
-        mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u);
-        uint32_t u = sm.rec_meta[rb * 4 + 0];
-        const uint32_t row0 = sm.rec_meta[rb * 4 + 2];
-        const uint32_t ex = sm.rec_meta[rb * 4 + 3];
+        PROF_WAIT(w_rec, mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u));
+        uint32_t u = sm.rec_meta[rb * META + M_UNION];
+        if (NSCAN == 2) u |= sm.rec_meta[rb * META + M_UNION + 1];
+        const uint32_t row0 = sm.rec_meta[rb * META + M_ROW0];
+        const uint32_t ex = sm.rec_meta[rb * META + M_EXIT];
         mbar_arrive(&sm.rec_empty[rb]);
         if (ex) break;
         while (u) {
             // one ring slot = up to GR rows of this record, one expect_tx for all of them
             const uint32_t slot = ri & (NGS - 1);
             const uint32_t cnt = min((uint32_t)__popc(u), (uint32_t)GR);
-            mbar_wait(&sm.empty[slot], ((ri / NGS) & 1u) ^ 1u);
+            PROF_WAIT(w_empty, mbar_wait(&sm.empty[slot], ((ri / NGS) & 1u) ^ 1u));
             mbar_expect_tx(&sm.full[slot], cnt * (uint32_t)ld * 4u);
             for (uint32_t j = 0; j < cnt; ++j) {
                 const int a = __ffs(u) - 1;
@@ -358,6 +397,9 @@ __device__ __forceinline__ void tile_producer(const TileSmem &sm, const float *_
         }
         ++r;
     }
+#ifdef QBM_TILE_PROF
+    PROF_PUT(16, (uint32_t)clock() - t_start); PROF_PUT(17, w_rec); PROF_PUT(18, w_empty);
+#endif
 }
 
 // ---- bounds warp: min(thr, -ln(u/2^32)/beta) for every (variable, chain) of the next window -------------
@@ -418,14 +460,23 @@ __device__ __forceinline__ void scan_prefetch(float *D, const float *__restrict_
     cp_async_commit();
 }
 
+__device__ __forceinline__ void scanners_sync() { asm volatile("bar.sync 2, %0;" ::"n"(NSCAN * 32) : "memory"); }
+
+// scanner `wsc` decides the proposals of chains wsc * TS .. wsc * TS + TS - 1; lane = chain tc + TS * part, a part = TS
+// consecutive variables of the 32-variable sub-window
 __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams &p, const float *__restrict__ Jn, const float *__restrict__ betas,
-                             int W, int nlive, int lane)
+                             int W, int nlive, int lane, int wsc)
 {
+    constexpr int Q4 = TS / 4;                        // 128-bit loads per row of this lane's part
+    constexpr uint32_t TSMASK = TS == 32 ? 0xffffffffu : ((1u << TS) - 1u);
     const int n = p.n;
     const int S = (n + 31) >> 5;
-    const int tc = lane & 15, hf = lane >> 4;
-    const bool alive = tc < nlive, h0 = hf == 0;
+    const int tc = lane % TS, part = lane / TS;
+    const int t = wsc * TS + tc;                      // this lane's chain of the tile
+    const bool alive = t < nlive, p0 = part == 0;
+    const int nlive_w = max(0, min(TS, nlive - wsc * TS));
     const bool vec16 = ((p.ldj & 3) == 0) && ((reinterpret_cast<uintptr_t>(Jn) & 15u) == 0);
+    float *const Dw = sm.Dbuf + wsc * (2 * 64 * 32);  // this scanner's copy of the coupling blocks
     uint32_t r = 0;                                   // record counter
     // what the previous record did to this lane's chain: rows, signs and magnitude of its coefficients
     uint32_t prev_mask = 0u, prev_neg = 0u, prev_union = 0u;
@@ -437,30 +488,31 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
         mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
         const int rem = n - s * 32;
         const uint32_t live = rem >= 32 ? FULL : ((1u << rem) - 1u);
-        float2 *crow = reinterpret_cast<float2 *>(sm.Cbuf) + (size_t)(rb * 32 + lane) * T;     // lane = row a of the panel
+        float *crow = sm.Cbuf + (size_t)(rb * 32 + lane) * T + wsc * TS;     // lane = row a of the panel
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const float c = ((sm.spinw[s * T + t] >> lane) & 1u) ? 1.0f : -1.0f;
-            crow[t] = make_float2(c, c);
-        }
+        for (int j = 0; j < TS; ++j) crow[j] = ((sm.spinw[s * T + wsc * TS + j] >> lane) & 1u) ? 1.0f : -1.0f;
         if (lane == 0) {
-            sm.rec_meta[rb * 4 + 0] = live;
-            sm.rec_meta[rb * 4 + 1] = 0xffffffffu;                       // dense
-            sm.rec_meta[rb * 4 + 2] = (uint32_t)(s * 32);
-            sm.rec_meta[rb * 4 + 3] = 0u;
+            sm.rec_meta[rb * META + M_UNION + wsc] = live;
+            sm.rec_meta[rb * META + M_COUNT + wsc] = DENSE_MARK;                   // dense
+            sm.rec_meta[rb * META + M_ROW0] = (uint32_t)(s * 32);                  // (every scanner writes the same value)
+            sm.rec_meta[rb * META + M_EXIT] = 0u;
         }
-        prev_union = live; prev_mask = live; prev_neg = ~sm.spinw[s * T + tc]; prev_mag = 1.0f;
+        prev_union = live; prev_mask = live; prev_neg = ~sm.spinw[s * T + t]; prev_mag = 1.0f;
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.rec_full[rb]);
     }
 
     // ---- annealing ----
+    PROF_VAR(w_fx); PROF_VAR(w_bnd); PROF_VAR(w_rece); PROF_VAR(w_cp); PROF_VAR(c_catch); PROF_VAR(c_scan);
+#ifdef QBM_TILE_PROF
+    const uint32_t t_start = (uint32_t)clock();
+#endif
     unsigned long long nacc = 0ull;
     uint32_t t_sweep = 0, e = 0, wi = 0;
     const unsigned long long hot_min =
         p.hot_fraction > 0.0f ? (unsigned long long)((double)p.hot_fraction * (double)n * (double)nlive) : 0ull;
     bool handed_over = false;
-    if (p.num_betas > 0) scan_prefetch(sm.Dbuf, Jn, p.ldj, n, S - 1, 0, lane, vec16);
+    if (p.num_betas > 0) scan_prefetch(Dw, Jn, p.ldj, n, S - 1, 0, lane, vec16);
     for (int b = 0; b < p.num_betas && !handed_over; ++b) {
         const float beta = __ldg(betas + b);
         const float thr = __fdiv_rn(44.36142f, beta);
@@ -469,30 +521,33 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
             for (int s = 0; s < S; ++s, ++r, ++e) {
                 const int k = s & 3;
                 const uint32_t rb = r & (NREC - 1), eb = e & 1u;
-                const float *D = sm.Dbuf + eb * (64 * 32);
+                const float *D = Dw + eb * (64 * 32);
                 // blocks of this sub-window have landed; fetch the next one's (the last prefetch of a launch is unused)
-                cp_async_wait_all();
+                PROF_WAIT(w_cp, cp_async_wait_all());
                 __syncwarp();
-                scan_prefetch(sm.Dbuf + (eb ^ 1u) * (64 * 32), Jn, p.ldj, n, s, (s + 1 == S) ? 0 : s + 1, lane, vec16);
+                scan_prefetch(Dw + (eb ^ 1u) * (64 * 32), Jn, p.ldj, n, s, (s + 1 == S) ? 0 : s + 1, lane, vec16);
                 // exported fields: every flip up to record r-2 applied
-                float G[16];
-                mbar_wait(&sm.fx_full[eb], (e >> 1) & 1u);
+                float G[TS];
+                PROF_WAIT(w_fx, mbar_wait(&sm.fx_full[eb], (e >> 1) & 1u));
                 {
-                    const float *fx = sm.Fx + eb * FXLD + hf * (16 * T + 16) + tc;
+                    const float *fx = sm.Fx + eb * FXLD + part * (TS * T + TS) + t;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) G[i] = fx[i * T];
+                    for (int i = 0; i < TS; ++i) G[i] = fx[i * T];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.fx_empty[eb]);
                 // record r-1 applied here, ahead of the appliers: same rows, same order, same coefficients
+#ifdef QBM_TILE_PROF
+                const uint32_t t_catch0 = (uint32_t)clock();
+#endif
                 {
-                    const uint32_t off_s = smem_u32(D) + (uint32_t)hf * 64u;
+                    const uint32_t off_s = smem_u32(D) + (uint32_t)part * (TS * 4u);
 #pragma unroll 4
                     for (int a = 0; a < 32; ++a) {
                         if (!((prev_union >> a) & 1u)) continue;                              // warp-uniform
                         const float c = ((prev_mask >> a) & 1u) ? (((prev_neg >> a) & 1u) ? -prev_mag : prev_mag) : 0.0f;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
+                        for (int q4 = 0; q4 < Q4; ++q4) {
                             const float4 d = lds128(off_s + (uint32_t)(a * 32 + q4 * 4) * 4u);
                             G[4 * q4 + 0] = __fmaf_rn(c, d.x, G[4 * q4 + 0]);
                             G[4 * q4 + 1] = __fmaf_rn(c, d.y, G[4 * q4 + 1]);
@@ -501,68 +556,91 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
                         }
                     }
                 }
-                const uint32_t old = sm.spinw[s * T + tc];
+#ifdef QBM_TILE_PROF
+                c_catch += (uint32_t)clock() - t_catch0;
+#endif
+                const uint32_t old = sm.spinw[s * T + t];
                 const int rem = n - s * 32;
                 // ---- pre-check: can any chain accept anything here (dE < 44.36142/beta)? ----
                 bool cand = false;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int a = hf * 16 + i;
+                for (int i = 0; i < TS; ++i) {
+                    const int a = part * TS + i;
                     const float dE = __fmul_rn(G[i], ((old >> a) & 1u) ? -2.0f : 2.0f);
                     cand |= (a < rem) && (dE < thr);
                 }
                 cand = __any_sync(FULL, cand && alive);
-                if (k == 0) mbar_wait(&sm.bnd_full[wi & 1u], (wi >> 1) & 1u);
-                mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
+                if (k == 0) PROF_WAIT(w_bnd, mbar_wait(&sm.bnd_full[wi & 1u], (wi >> 1) & 1u));
+                PROF_WAIT(w_rece, mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u));
+#ifdef QBM_TILE_PROF
+                const uint32_t t_scan0 = (uint32_t)clock();
+#endif
                 uint32_t flipm = 0u;
                 if (cand) {
-                    // ---- scan (lane = chain tc + 16 * half; 16 variables of the sub-window per lane) ----
-                    // this lane's bound of variable a (its own half only): a load per step, independent of the decisions
-                    const float *bo = sm.bounds + (wi & 1u) * (4 * 32 * T) + (k * 32 + hf * 16) * T + tc;
-                    const uint32_t dbuf_s = smem_u32(D) + (uint32_t)(32 * 32) * 4u + (uint32_t)hf * 64u;
-                    const uint32_t cbuf_s = smem_u32(sm.Cbuf) + (uint32_t)(rb * 32 * T + tc) * 8u;
+                    // ---- scan (lane = chain tc + TS * part; TS variables of the sub-window per lane) ----
+                    // this lane's bound of variable a (its own part only): a load per step, independent of the decisions
+                    const float *bo = sm.bounds + (wi & 1u) * (4 * 32 * T) + (k * 32 + part * TS) * T + t;
+                    const uint32_t dbuf_s = smem_u32(D) + (uint32_t)(32 * 32) * 4u + (uint32_t)part * (TS * 4u);
+                    const uint32_t cbuf_s = smem_u32(sm.Cbuf) + (uint32_t)(rb * 32 * T + t) * 4u;
+                    const uint32_t rmask_s = smem_u32(sm.rowmask) + (uint32_t)(rb * 32) * 4u + (uint32_t)wsc * (4u / NSCAN);
                     // branch-free: every step applies c * D[a][.] with c = 0 for chains that keep variable a; the
                     // shared-memory reads do not depend on the decisions (row a+1 is fetched before the vote of row a),
                     // only field -> dE -> compare -> ballot -> c -> fma is a dependent chain
-                    float4 dcur[4], dnxt[4];
+                    float4 dcur[Q4], dnxt[Q4];
 #pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = lds128(dbuf_s + (uint32_t)(q4 * 4) * 4u);
+                    for (int q4 = 0; q4 < Q4; ++q4) dcur[q4] = lds128(dbuf_s + (uint32_t)(q4 * 4) * 4u);
 #pragma unroll
                     for (int a = 0; a < 32; ++a) {
-                        const int ha = a >> 4, i = a & 15;
+                        const int pa = a / TS, i = a % TS;
                         if (a < 31) {
 #pragma unroll
-                            for (int q4 = 0; q4 < 4; ++q4) dnxt[q4] = lds128(dbuf_s + (uint32_t)((a + 1) * 32 + q4 * 4) * 4u);
+                            for (int q4 = 0; q4 < Q4; ++q4) dnxt[q4] = lds128(dbuf_s + (uint32_t)((a + 1) * 32 + q4 * 4) * 4u);
                         }
                         const float sg = ((old >> a) & 1u) ? -2.0f : 2.0f;        // variable a has not been visited yet
                         const float dE = __fmul_rn(G[i], sg);
-                        const bool acc = ((ha == 0) == h0) & alive & (a < rem) & ((dE <= 0.0f) | (dE < bo[i * T]));
+                        const bool acc = (part == pa) & alive & (a < rem) & ((dE <= 0.0f) | (dE < bo[i * T]));
                         const uint32_t bal = __ballot_sync(FULL, acc);
                         const uint32_t oldbal = __ballot_sync(FULL, (old >> a) & 1u);          // off the dependent chain
-                        if (lane == 0) sm.rowmask[rb * 32 + a] = ((bal >> (16 * ha)) & 0xffffu) | (oldbal << 16);
-                        const bool mine = (bal >> (16 * ha + tc)) & 1u;
+                        if (lane == 0) {
+                            const uint32_t w = ((bal >> (TS * pa)) & TSMASK) | ((oldbal & TSMASK) << TS);
+                            if (NSCAN == 1) asm volatile("st.shared.u32 [%0], %1;" ::"r"(rmask_s + (uint32_t)a * 4u), "r"(w) : "memory");
+                            else asm volatile("st.shared.u16 [%0], %1;" ::"r"(rmask_s + (uint32_t)a * 4u), "h"((unsigned short)w) : "memory");
+                        }
+                        const bool mine = (bal >> (TS * pa + tc)) & 1u;
                         const float c = mine ? sg : 0.0f;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) {
+                        for (int q4 = 0; q4 < Q4; ++q4) {
                             G[4 * q4 + 0] = __fmaf_rn(c, dcur[q4].x, G[4 * q4 + 0]);
                             G[4 * q4 + 1] = __fmaf_rn(c, dcur[q4].y, G[4 * q4 + 1]);
                             G[4 * q4 + 2] = __fmaf_rn(c, dcur[q4].z, G[4 * q4 + 2]);
                             G[4 * q4 + 3] = __fmaf_rn(c, dcur[q4].w, G[4 * q4 + 3]);
                         }
-                        if (h0) asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(cbuf_s + (uint32_t)a * (T * 8u)), "f"(c) : "memory");
+                        if (p0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbuf_s + (uint32_t)a * (T * 4u)), "f"(c) : "memory");
                         flipm |= (mine ? 1u : 0u) << a;
 #pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4) dcur[q4] = dnxt[q4];
+                        for (int q4 = 0; q4 < Q4; ++q4) dcur[q4] = dnxt[q4];
                     }
+                } else if (NSCAN > 1) {
+                    // nothing to decide for these chains, but another scanner's chains may flip rows of this record: the
+                    // appliers then read this scanner's coefficients and mask halves too (lane = row a)
+                    const uint32_t cz = smem_u32(sm.Cbuf) + (uint32_t)((rb * 32 + lane) * T + wsc * TS) * 4u;
+#pragma unroll
+                    for (int j = 0; j < TS / 4; ++j)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(cz + (uint32_t)j * 16u), "f"(0.0f) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(smem_u32(sm.rowmask) + (uint32_t)(rb * 32 + lane) * 4u + (uint32_t)wsc * 2u),
+                                 "h"((unsigned short)0) : "memory");
                 }
+#ifdef QBM_TILE_PROF
+                c_scan += (uint32_t)clock() - t_scan0;
+#endif
                 const uint32_t unionm = __reduce_or_sync(FULL, flipm);
-                const uint32_t cnt = __reduce_add_sync(FULL, h0 ? (uint32_t)__popc(flipm) : 0u);
-                if (h0) sm.spinw[s * T + tc] = old ^ flipm;
+                const uint32_t cnt = __reduce_add_sync(FULL, p0 ? (uint32_t)__popc(flipm) : 0u);
+                if (p0) sm.spinw[s * T + t] = old ^ flipm;
                 if (lane == 0) {
-                    sm.rec_meta[rb * 4 + 0] = unionm;
-                    sm.rec_meta[rb * 4 + 1] = cnt;
-                    sm.rec_meta[rb * 4 + 2] = (uint32_t)(s * 32);
-                    sm.rec_meta[rb * 4 + 3] = 0u;
+                    sm.rec_meta[rb * META + M_UNION + wsc] = unionm;
+                    sm.rec_meta[rb * META + M_COUNT + wsc] = cnt;
+                    sm.rec_meta[rb * META + M_ROW0] = (uint32_t)(s * 32);
+                    sm.rec_meta[rb * META + M_EXIT] = 0u;
                 }
                 __syncwarp();
                 if (lane == 0) {
@@ -574,33 +652,51 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
                 prev_union = unionm; prev_mask = flipm; prev_neg = old; prev_mag = 2.0f;
             }
             // two-phase schedule: once a sweep accepts less than hot_fraction of its proposals the chains are cheaper to
-            // advance one warp each (rows no longer shared by most chains)
-            if (hot_min > 0ull && nacc - nacc_before < hot_min) handed_over = true;
+            // advance one warp each (rows no longer shared by most chains); the scanners add up their counts (one
+            // rendezvous per sweep) and take the same decision
+            if (hot_min > 0ull) {
+                unsigned long long flips = nacc - nacc_before;
+                if (NSCAN > 1) {
+                    volatile uint32_t *cw = sm.ctl + 1 + (t_sweep & 1u) * NSCAN;
+                    if (lane == 0) cw[wsc] = (uint32_t)flips;
+                    scanners_sync();
+                    flips = 0ull;
+#pragma unroll
+                    for (int j = 0; j < NSCAN; ++j) flips += cw[j];
+                }
+                if (flips < hot_min) handed_over = true;
+            }
         }
     }
     cp_async_wait_all();
+#ifdef QBM_TILE_PROF
+    if (lane == 0 && wsc == 0) {
+        PROF_PUT(8, (uint32_t)clock() - t_start); PROF_PUT(9, w_fx); PROF_PUT(10, w_bnd); PROF_PUT(11, w_rece); PROF_PUT(12, w_cp);
+        PROF_PUT(13, c_catch); PROF_PUT(14, c_scan);
+    }
+#endif
     // ---- exit record; the flag stops the bounds warp, which polls it while it waits for a free buffer ----
     {
         const uint32_t rb = r & (NREC - 1);
         mbar_wait(&sm.rec_empty[rb], ((r / NREC) & 1u) ^ 1u);
         if (lane == 0) {
-            sm.rec_meta[rb * 4 + 0] = 0u;
-            sm.rec_meta[rb * 4 + 1] = 0u;
-            sm.rec_meta[rb * 4 + 2] = 0u;
-            sm.rec_meta[rb * 4 + 3] = 1u;
+            sm.rec_meta[rb * META + M_UNION + wsc] = 0u;
+            sm.rec_meta[rb * META + M_COUNT + wsc] = 0u;
+            sm.rec_meta[rb * META + M_ROW0] = 0u;
+            sm.rec_meta[rb * META + M_EXIT] = 1u;
             *reinterpret_cast<volatile uint32_t *>(sm.ctl) = 1u;
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.rec_full[rb]);
     }
     if (lane == 0) {
-        if (p.sweeps_done != nullptr) p.sweeps_done[blockIdx.x] = t_sweep;      // completed sweeps of this tile
+        if (p.sweeps_done != nullptr && wsc == 0) p.sweeps_done[blockIdx.x] = t_sweep;      // completed sweeps of this tile
         if (p.counters != nullptr) {
             atomicAdd(p.counters + 0, nacc);
-            atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)t_sweep * (unsigned long long)nlive);
+            atomicAdd(p.counters + 1, (unsigned long long)n * (unsigned long long)t_sweep * (unsigned long long)nlive_w);
         }
     }
-    tile_sync((W + 1) * 32);          // spins final: the appliers write the states
+    tile_sync((W + NSCAN) * 32);      // spins final: the appliers write the states
 }
 
 // NS == 8 (n > 1024): W = windows / 2 applier warps x 8 columns; NS == 4 (n <= 1024): W = windows applier warps x 4 columns.
@@ -624,10 +720,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NGS; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], (uint32_t)W); }
-        for (int i = 0; i < NREC; ++i) { mbar_init(&sm.rec_full[i], 1); mbar_init(&sm.rec_empty[i], (uint32_t)W + 1u); }
+        for (int i = 0; i < NREC; ++i) { mbar_init(&sm.rec_full[i], NSCAN); mbar_init(&sm.rec_empty[i], (uint32_t)W + 1u); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&sm.fx_full[i], 1); mbar_init(&sm.fx_empty[i], 1);
-            mbar_init(&sm.bnd_full[i], 1); mbar_init(&sm.bnd_empty[i], 1);
+            mbar_init(&sm.fx_full[i], 1); mbar_init(&sm.fx_empty[i], NSCAN);
+            mbar_init(&sm.bnd_full[i], 1); mbar_init(&sm.bnd_empty[i], NSCAN);
         }
         sm.ctl[0] = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -640,9 +736,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             if (lane == 0) tile_producer(sm, Jp, ld);
         } else if (warp == WARP_BOUNDS) {
             tile_bounds(sm, p, betas, chain0, lane);
-        } else if (warp == WARP_SCANNER) {
-            tile_sync((W + 1) * 32);                    // initial spins written
-            tile_scanner(sm, p, p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj, betas, W, nlive, lane);
+        } else if (scanner_of_warp(warp) >= 0) {
+            tile_sync((W + NSCAN) * 32);                // initial spins written
+            tile_scanner(sm, p, p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj, betas, W, nlive, lane, scanner_of_warp(warp));
         }
         return;
     }
@@ -679,7 +775,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             sm.spinw[s * T + t] = (t < nlive) ? wd : 0u;
         }
     }
-    tile_sync((W + 1) * 32);                            // the scanner takes the spins from here on
+    tile_sync((W + NSCAN) * 32);                        // the scanners take the spins from here on
 
     f32x2 F2[NS / 2][T];       // F2[jw*2 + h][t] = packed fields of sub-windows (2h, 2h+1) of window jw, chain t
 #pragma unroll
@@ -698,6 +794,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     A.rowmask = smem_u32(sm.rowmask);
 
     // ---- records: S initial-field records, then one per sub-window and sweep, until the exit record ----
+    PROF_VAR(w_ring); PROF_VAR(w_recf); PROF_VAR(w_fxe);
+#ifdef QBM_TILE_PROF
+    const uint32_t t_start = (uint32_t)clock();
+#else
+    uint32_t w_ring = 0u;      // (unused outside the profiling build)
+#endif
     uint32_t gi = 0;
     int s_next = 0;                                     // sub-window of record r + 1 once annealing has started
     for (uint32_t r = 0;; ++r) {
@@ -708,8 +810,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             const int g1 = s_next >> 2, k1s = s_next & 3;
             if (g1 % W == warp) {
                 const int slot = (g1 / W) * 4 + k1s;
-                mbar_wait(&sm.fx_empty[e1 & 1u], ((e1 >> 1) & 1u) ^ 1u);
-                float4 *dst = reinterpret_cast<float4 *>(sm.Fx + (e1 & 1u) * FXLD + lane * T + (lane >> 4) * 16);
+                PROF_WAIT(w_fxe, mbar_wait(&sm.fx_empty[e1 & 1u], ((e1 >> 1) & 1u) ^ 1u));
+                // [column][chain]; the columns of part q shifted by q * TS floats: the scanners' reads are conflict-free
+                float4 *dst = reinterpret_cast<float4 *>(sm.Fx + (e1 & 1u) * FXLD + lane * T + (lane / TS) * TS);
                 // register arrays need static indices: one copy of the four stores per column slot, the slot is warp-uniform
 #pragma unroll
                 for (int j = 0; j < NS; ++j)
@@ -725,14 +828,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
             s_next = (s_next + 1 == S) ? 0 : s_next + 1;
         }
         const uint32_t rb = r & (NREC - 1);
-        mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u);
-        const uint32_t u = sm.rec_meta[rb * 4 + 0], cnt = sm.rec_meta[rb * 4 + 1], ex = sm.rec_meta[rb * 4 + 3];
+        PROF_WAIT(w_recf, mbar_wait(&sm.rec_full[rb], (r / NREC) & 1u));
+        uint32_t u = sm.rec_meta[rb * META + M_UNION], cnt = sm.rec_meta[rb * META + M_COUNT];
+        if (NSCAN == 2) { u |= sm.rec_meta[rb * META + M_UNION + 1]; cnt += sm.rec_meta[rb * META + M_COUNT + 1]; }
+        const uint32_t ex = sm.rec_meta[rb * META + M_EXIT];
         if (ex) break;
-        if (u != 0u) apply_record<NS>(F2, A, u, cnt, rb, lane, gi, dense_min);
+        if (u != 0u) apply_record<NS>(F2, A, u, cnt, rb, lane, gi, dense_min, w_ring);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.rec_empty[rb]);
     }
 
+#ifdef QBM_TILE_PROF
+    if (lane == 0) {      // per applier warp: total, waits for ring slots / records / the export buffer
+        PROF_PUT(0, (uint32_t)clock() - t_start); PROF_PUT(1, w_ring); PROF_PUT(2, w_recf); PROF_PUT(3, w_fxe);
+        if (warp == 0) { PROF_PUT(4, (uint32_t)clock() - t_start); PROF_PUT(5, w_ring); PROF_PUT(6, w_recf); PROF_PUT(7, w_fxe); }
+    }
+#endif
     if (p.fields != nullptr) {
         // fields in the warp kernel's layout: chain-major, float4 (sub-windows 0..3) per lane and 128-variable window
 #pragma unroll
@@ -747,7 +858,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     }
 
     // ---- write-back: states in natural variable order, 0/1 ----
-    tile_sync((W + 1) * 32);
+    tile_sync((W + NSCAN) * 32);
     for (int t = warp; t < nlive; t += W) {
         int8_t *o = p.out + (size_t)(cl0 + t) * (size_t)n;
         for (int s = 0; s < S; ++s) {
@@ -794,3 +905,17 @@ int sa_tile_launch(const SaParams &p, cudaStream_t st)
     if (win <= 8) return launch_tile<4>(p, win, st);                       // n <= 1024: W = win applier warps x 4 columns
     return launch_tile<8>(p, win / 2, st);                                 // n >  1024: W = win / 2 applier warps x 8 columns
 }
+
+#ifdef QBM_TILE_PROF
+// profiling build only: read (and clear) the wait-clock counters of the chain-tile kernel
+extern "C" QBM_API int qbm_debug_tile_prof(unsigned long long *out32, int reset)
+{
+    QBM_CUDA_OK(cudaDeviceSynchronize());
+    if (out32) QBM_CUDA_OK(cudaMemcpyFromSymbol(out32, g_tile_prof, sizeof(unsigned long long) * 32));
+    if (reset) {
+        unsigned long long z[32] = {};
+        QBM_CUDA_OK(cudaMemcpyToSymbol(g_tile_prof, z, sizeof(z)));
+    }
+    return QBM_OK;
+}
+#endif
