@@ -124,7 +124,7 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
         SaParams hot = p;
         hot.fields = hp + (size_t)batch_q * (size_t)ld;
         hot.sweeps_done = reinterpret_cast<uint32_t *>(hot.fields + (size_t)p.total_chains * (size_t)ld);
-        hot.hot_fraction = pct ? (float)pct / 100.0f : 0.55f;
+        hot.hot_fraction = pct ? (float)pct / 100.0f : 0.50f;
         if (const int rc = sa_tile_launch(hot, st)) return rc;
         // the resuming instantiation (RS) starts from fields / sweeps_done / init instead of computing the initial fields
         p.fields = hot.fields; p.sweeps_done = hot.sweeps_done;
