@@ -172,6 +172,12 @@ int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, floa
                      const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
                      unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
                      void *stream);
+/* The same step with the step counter in device memory (draws are keyed by step + *step_dev): a CUDA graph captured around
+ * this call advances through the Philox streams when the caller increments the counter between replays. */
+int qbm_rbm_cd1_step_dev(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                         const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                         unsigned long long seed, unsigned int step, const unsigned int *step_dev, void *workspace,
+                         size_t workspace_bytes, void *stream);
 
 /* Data-parallel form of the two steps (minibatch rows sharded over the GPUs, ONE all-reduce of the
  * parameter-shaped statistics, identical update on every rank).  The gradient variants leave the parameters untouched and

@@ -48,6 +48,7 @@ SIGNATURES = {
     "qbm_rbm_class_given_x": (_c_i, [_c_p, _c_p, _c_p, _c_p, _c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_disc_step": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [ctypes.c_float] * 3 + [_c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_cd1_step": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [ctypes.c_float] * 2 + [_c_u64, _c_u, _c_p, _c_sz, _c_p]),
+    "qbm_rbm_cd1_step_dev": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [ctypes.c_float] * 2 + [_c_u64, _c_u, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_grad_count": (_c_sz, [_c_i, _c_i, _c_i]),
     "qbm_rbm_disc_grad": (_c_i, [_c_p] * 6 + [_c_i] * 4 + [_c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_cd1_grad": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [_c_u64, _c_u, _c_p, _c_p, _c_sz, _c_p]),

@@ -13,6 +13,7 @@ struct EpiParams {
     float alpha, beta;
     int act;                              // 0 = identity, 1 = sigmoid
     unsigned long long seed; unsigned int stream;   // Philox key / stream id for the sample
+    const unsigned int *step_dev;         // nullable: device-resident step counter, stream id += 4 * *step_dev (CUDA-graph replays)
 };
 
 // C[M,N] = epi(alpha * A[M,K] . B[N,K]^T), both operands row-major with K contiguous

@@ -11,18 +11,21 @@
 //   x^T.D      : A = x^T [V,B], B = D^T [H,B]      (epilogue: W += lr/B * acc)
 #include "gemm.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace {
 
 constexpr int BM = 128;          // rows of A per CTA  (= UMMA M, TMEM lanes)
-// BN = rows of B per CTA (= UMMA N, TMEM columns) is a template parameter: 128, or 256 for problems large enough
-// to fill the 148 SMs with 128 x 256 tiles (twice the MMA work per byte staged)
+// BN = rows of B per CTA (= UMMA N, TMEM columns) is a template parameter: the widest of 256 / 128 / 64 / 32 that still gives
+// every SM a tile (256: twice the MMA work per byte staged; 32: a training step at batch 256 is a handful of tiles, and
+// the time of such a launch is the epilogue of ONE tile -- 128 threads x BN columns each -- plus the depth of the K loop,
+// so narrow tiles on many SMs and a deeper TMA ring (8 stages) cut it from ~30 us to the launch floor)
 constexpr int BK = 32;           // K elements per stage: 32 x 4 B = one 128-byte swizzle row
 constexpr int UMMA_K = 8;        // K per tcgen05.mma for tf32 (32 bytes)
-constexpr int STAGES = 4;
 constexpr int A_TILE_BYTES = BM * BK * 4;                     // 16 KB per stage
+template <int BN> __host__ __device__ constexpr int n_stages() { return BN <= 64 ? 8 : 4; }
 template <int BN> __host__ __device__ constexpr int stage_bytes() { return A_TILE_BYTES + BN * BK * 4; }
-template <int BN> __host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<BN>() + 1024; }   // + slack for 1024-byte alignment
+template <int BN> __host__ __device__ constexpr int smem_bytes() { return n_stages<BN>() * stage_bytes<BN>() + 1024; }   // + slack for 1024-byte alignment
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -90,6 +93,7 @@ __global__ void __launch_bounds__(128, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                  int M, int N, int K)
 {
+    constexpr int STAGES = n_stages<BN>();
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], done_bar;
@@ -154,6 +158,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool row_ok = m < M;
     const float *tabrow = (ep.rowtab != nullptr && row_ok) ? ep.rowtab + (size_t)ep.ridx[m] * ep.ldtab : nullptr;
     const uint32_t k0 = (uint32_t)ep.seed, k1 = (uint32_t)(ep.seed >> 32);
+    const uint32_t strm = ep.stream + (ep.step_dev != nullptr ? 4u * __ldg(ep.step_dev) : 0u);
     const bool vecc = ep.C != nullptr && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
     const bool vecs = ep.S != nullptr && (ep.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.S) & 15) == 0;
     const bool vecin = ep.Cin != nullptr && (ep.ldcin & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.Cin) & 15) == 0;
@@ -177,7 +182,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j4 = 0; j4 < 8; ++j4) {
             Philox4 u4 = {0u, 0u, 0u, 0u};
             if (ep.S != nullptr || ep.St != nullptr)
-                u4 = philox4x32_10((uint32_t)m, (uint32_t)((nb >> 2) + j4), ep.stream, 0x52424Du, k0, k1);
+                u4 = philox4x32_10((uint32_t)m, (uint32_t)((nb >> 2) + j4), strm, 0x52424Du, k0, k1);
             const uint32_t us[4] = {u4.x, u4.y, u4.z, u4.w};
             // a lane owns 4 consecutive columns of its row here: the row-major outputs (C, S) and Cin move as one
             // 16-byte access per lane when the addresses allow it (rows of a warp are ld apart, so a 4-byte store per
@@ -294,26 +299,39 @@ int qbm_gemm_tf32_launch(const float *A, long long lda, const float *B, long lon
     QBM_CHECK_ARG(lda >= K && ldb >= K && lda % 4 == 0 && ldb % 4 == 0,
                   "qbm_gemm_tf32: leading dimensions must be >= K and multiples of 4 floats (TMA needs 16-byte row strides)");
     QBM_CHECK_ARG(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, "qbm_gemm_tf32: operands must be 16-byte aligned");
-    // 128 x 256 tiles when they alone give every SM a CTA, else 128 x 128
-    const long long tiles256 = (long long)((M + BM - 1) / BM) * ((N + 255) / 256);
-    const bool wide = tiles256 >= 148;
+    // the widest tile that still gives every SM a CTA; problems smaller than that take the narrowest
+    const long long mt = (M + BM - 1) / BM;
+    int bn = 32;
+    for (int cand : {256, 128, 64})
+        if (mt * ((N + cand - 1) / cand) >= 148) { bn = cand; break; }
+    if (const char *e = getenv("QBM_GEMM_BN")) {            // measurement aid (tools/probe_gemm.py): force a tile width
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128 || v == 256) bn = v;
+    }
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, A, M, K, lda, BM);
     if (rc) return rc;
-    rc = make_map(&tmB, B, N, K, ldb, wide ? 256 : 128);
+    rc = make_map(&tmB, B, N, K, ldb, bn);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
-        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
-        attr_set = true;
-    }
-    if (wide) {
-        dim3 grid((unsigned)((N + 255) / 256), (unsigned)((M + BM - 1) / BM));
-        gemm_tf32_kernel<256><<<grid, 128, smem_bytes<256>(), st>>>(tmA, tmB, ep, M, N, K);
-    } else {
-        dim3 grid((unsigned)((N + 127) / 128), (unsigned)((M + BM - 1) / BM));
-        gemm_tf32_kernel<128><<<grid, 128, smem_bytes<128>(), st>>>(tmA, tmB, ep, M, N, K);
+    const dim3 grid((unsigned)((N + bn - 1) / bn), (unsigned)mt);
+    // the attribute belongs to the current device (a process may drive several), so it is set per launch
+    switch (bn) {
+        case 256:
+            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
+            gemm_tf32_kernel<256><<<grid, 128, smem_bytes<256>(), st>>>(tmA, tmB, ep, M, N, K);
+            break;
+        case 128:
+            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
+            gemm_tf32_kernel<128><<<grid, 128, smem_bytes<128>(), st>>>(tmA, tmB, ep, M, N, K);
+            break;
+        case 64:
+            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()));
+            gemm_tf32_kernel<64><<<grid, 128, smem_bytes<64>(), st>>>(tmA, tmB, ep, M, N, K);
+            break;
+        default:
+            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32>()));
+            gemm_tf32_kernel<32><<<grid, 128, smem_bytes<32>(), st>>>(tmA, tmB, ep, M, N, K);
+            break;
     }
     QBM_LAUNCH_OK("gemm_tf32_kernel");
     return QBM_OK;

@@ -172,7 +172,8 @@ __global__ void rbm_disc_finish_kernel(float *__restrict__ b_c, float *__restric
 __global__ void __launch_bounds__(128) rbm_class_kernel(const float *__restrict__ Hm, long long ldh, const float *__restrict__ U,
                                                        long long ldu, const float *__restrict__ b_c, int H, int C,
                                                        float *__restrict__ P, long long ldp, int *__restrict__ y1,
-                                                       unsigned long long seed, unsigned int stream)
+                                                       unsigned long long seed, unsigned int stream,
+                                                       const unsigned int *__restrict__ step_dev = nullptr)
 {
     __shared__ float red[MAXC][4];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(128) rbm_class_kernel(const float *__restrict_
         for (int c = 0; c < C; ++c) { e[c] = __expf(red[c][0] + red[c][1] + red[c][2] + red[c][3] + b_c[c]); z += e[c]; }
         z = fmaxf(z, 1e-12f);                                   // torch.nn.functional.normalize eps
         float cum = 0.0f; int pick = C - 1; bool done = false;
-        const Philox4 u4 = philox4x32_10((uint32_t)b, 0u, stream, 0x434C53u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const unsigned int strm = stream + (step_dev != nullptr ? 4u * __ldg(step_dev) : 0u);
+        const Philox4 u4 = philox4x32_10((uint32_t)b, 0u, strm, 0x434C53u, (uint32_t)seed, (uint32_t)(seed >> 32));
         const float u = (float)(u4.x >> 8) * 5.9604644775390625e-8f;
         for (int c = 0; c < C; ++c) {
             const float p = e[c] / z;
@@ -473,20 +475,19 @@ extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b
     QBM_LAUNCH_OK("rbm_disc_update_kernel");
     rbm_disc_finish_kernel<<<1, 256, 0, st>>>(b_c, b_v, probs, lC, y, B, C, V, scale, sparse_constant, pred, loss, 1);
     QBM_LAUNCH_OK("rbm_disc_finish_kernel");
-    // W += scale * x^T.D   (SGD update fused into the GEMM epilogue), then refresh W^T
+    // W += scale * x^T.D   (SGD update fused into the GEMM epilogue, which also writes the K-major copy W^T)
     EpiParams e2 = {};
-    e2.C = W; e2.ldc = lH; e2.Cin = W; e2.ldcin = lH; e2.alpha = scale; e2.beta = 1.0f;
-    if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.Dt, lB, V, H, B, e2, st)) return rc;
-    return transpose(W, lH, Wt, lV, V, H, st);
+    e2.C = W; e2.ldc = lH; e2.Cin = W; e2.ldcin = lH; e2.alpha = scale; e2.beta = 1.0f; e2.Ct = Wt; e2.ldct = lV;
+    return qbm_gemm_tf32_launch(w.xt, lB, w.Dt, lB, V, H, B, e2, st);
 }
 
 // CD-1 step composed from the primitives:
 //   h0 ~ Bern(R1(v0,y0)); v1 ~ Bern(R2(h0)); y1 ~ Cat(R3(h0)); ph1 = R1(v1,y1);
 //   dW = v0^T ph0 - v1^T ph1; dU = y0^T ph0 - y1^T ph1; db_v = sum(v0-v1); db_h = sum(ph0-ph1); db_c = sum(y0-y1)
-extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
-                                        const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
-                                        unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
-                                        void *stream)
+static int cd1_step_impl(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                         const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                         unsigned long long seed, unsigned int step, const unsigned int *step_dev, void *workspace,
+                         size_t workspace_bytes, void *stream)
 {
     if (int rc = check_dims("qbm_rbm_cd1_step", B, V, H, C)) return rc;
     QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && v0 && y0 && workspace, "qbm_rbm_cd1_step: null pointer argument");
@@ -498,14 +499,14 @@ extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_
     // positive phase: ph0 (+ transposed), h0 ~ Bernoulli(ph0)
     EpiParams e = {};
     e.C = w.p0; e.ldc = lH; e.Ct = w.p0t; e.ldct = lB; e.S = w.h0; e.lds = lH; e.bias_n = b_h; e.rowtab = U; e.ridx = y0;
-    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u;
+    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u; e.step_dev = step_dev;
     if (int rc = qbm_gemm_tf32_launch(v0, lV, Wt, lV, B, H, V, e, st)) return rc;
     // negative phase: v1 ~ Bernoulli(sigmoid(h0.W^T + b_v)) (+ transposed), y1 ~ Cat(p(y|h0))
     EpiParams e2 = {};
     e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
-    e2.stream = step * 4u + 1u;
+    e2.stream = step * 4u + 1u; e2.step_dev = step_dev;
     if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
-    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u);
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, step_dev);
     QBM_LAUNCH_OK("rbm_class_kernel");
     EpiParams e3 = {};
     e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
@@ -519,9 +520,29 @@ extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_
     EpiParams g1 = {};
     g1.C = W; g1.ldc = lH; g1.Cin = W; g1.ldcin = lH; g1.alpha = scale; g1.beta = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.p0t, lB, V, H, B, g1, st)) return rc;
-    g1.alpha = -scale;
-    if (int rc = qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st)) return rc;
-    return transpose(W, lH, Wt, lV, V, H, st);
+    g1.alpha = -scale; g1.Ct = Wt; g1.ldct = lV;              // the second accumulate also writes the K-major copy W^T
+    return qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st);
+}
+
+extern "C" QBM_API int qbm_rbm_cd1_step(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                                        const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                                        unsigned long long seed, unsigned int step, void *workspace, size_t workspace_bytes,
+                                        void *stream)
+{
+    return cd1_step_impl(W, Wt, U, b_v, b_h, b_c, v0, y0, B, V, H, C, lr, sparse_constant, seed, step, nullptr, workspace,
+                         workspace_bytes, stream);
+}
+
+// the same step with the step counter read from device memory: draws use step + *step_dev, so a captured CUDA graph of
+// this call advances through the Philox streams when the caller increments the counter between replays
+extern "C" QBM_API int qbm_rbm_cd1_step_dev(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *v0,
+                                            const int *y0, int B, int V, int H, int C, float lr, float sparse_constant,
+                                            unsigned long long seed, unsigned int step, const unsigned int *step_dev,
+                                            void *workspace, size_t workspace_bytes, void *stream)
+{
+    QBM_CHECK_ARG(step_dev, "qbm_rbm_cd1_step_dev: null step counter");
+    return cd1_step_impl(W, Wt, U, b_v, b_h, b_c, v0, y0, B, V, H, C, lr, sparse_constant, seed, step, step_dev, workspace,
+                         workspace_bytes, stream);
 }
 
 // ---- gradient variants of the two steps + the fused apply: what the data-parallel trainers run ------------------------

@@ -51,7 +51,7 @@ def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha=1.0, beta=0.0, Cin=None, b
 
 class B200ClassificationRBM:
     def __init__(self, num_visible, num_hidden, k, num_classes=2, learning_rate=0.05, sparse_constant=0.00,
-                 use_cuda=True, seed=42, device=None, process_group=None):
+                 use_cuda=True, seed=42, device=None, process_group=None, use_graphs=True):
         # same RNG protocol as the reference (:14-15, :26-30): CPU generators, then moved to the device
         np.random.seed(seed)
         torch.manual_seed(seed)
@@ -77,6 +77,12 @@ class B200ClassificationRBM:
         self._ws_key = None
         self._grad = None
         self._step = 0
+        # single-GPU training steps are a fixed sequence of ~7-10 small launches: from the second step of a given shape on
+        # they are replayed as one CUDA graph (static input / output buffers; the CD-1 step counter lives on the device)
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}
+        self._step_dev = None
+        self._step_dev_val = -1
         self.acc_per_epoch_list = []
         self.auc_per_epoch_list = []
 
@@ -115,6 +121,7 @@ class B200ClassificationRBM:
     def _workspace(self, B):
         key = B
         if self._ws_key != key:
+            self._graphs.clear()                # captured steps point into the old workspace
             L = _lib.load()
             nbytes = L.qbm_rbm_workspace_bytes(B, self.num_visible, self.num_hidden, self.num_classes)
             self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
@@ -173,6 +180,43 @@ class B200ClassificationRBM:
                    self.num_visible, self.num_hidden, self.num_classes, float(factor * self.learning_rate / global_batch),
                    float(self.sparse_constant), loss.data_ptr() if loss is not None else None, float(1.0 / global_batch))
 
+    # ---- CUDA-graph replay of the single-GPU steps -----------------------------------------------------------------
+    def _graph_entry(self, key, B, launch):
+        """None on the first step of a key (the caller runs it eagerly, which also warms the kernels up), afterwards the
+        captured step: static buffers x [B, ld4(V)], y int32 [B], out = [probs (B x ld4(C)) | loss] and pred int32 [B]."""
+        self._workspace(B)                      # (a new workspace drops every captured step)
+        # the captured launches hold raw pointers: a parameter tensor that was re-assigned (not updated in place) gets a new capture
+        key = key + tuple(t.data_ptr() for t in (self._W, self._Wt, self._U, self.visible_bias, self.hidden_bias, self.class_bias))
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = "warm"
+            return None
+        if ent == "warm":
+            V, C = self.num_visible, self.num_classes
+            ent = {"x": _padded(B, V, self.device), "y": torch.zeros(B, dtype=torch.int32, device=self.device),
+                   "out": torch.zeros(B * _ld4(C) + 4, dtype=torch.float32, device=self.device),
+                   "pred": torch.zeros(B, dtype=torch.int32, device=self.device)}
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.device(self.device), torch.cuda.graph(g, capture_error_mode="thread_local"):
+                launch(ent)
+            ent["graph"] = g
+            self._graphs[key] = ent
+        return ent
+
+    def _stage(self, ent, x, y, B):
+        V = self.num_visible
+        x = torch.as_tensor(x)
+        if x.dim() != 2 or tuple(x.shape) != (B, V):
+            raise ValueError(f"expected a [{B}, {V}] matrix, got {tuple(x.shape)}")
+        y = torch.as_tensor(y)
+        if y.dim() == 2:                       # one-hot rows
+            y = y.argmax(dim=1)
+        if tuple(y.shape) != (B,):
+            raise ValueError(f"expected {B} labels, got shape {tuple(y.shape)}")
+        ent["x"][:, :V].copy_(x, non_blocking=True)
+        ent["y"].copy_(y, non_blocking=True)   # (converts to int32 on the way)
+
     # ---- Gibbs primitives (:43-60) --------------------------------------------------------------------
     def sample_hidden(self, visible_activations, class_activations):
         L = _lib.load()
@@ -218,10 +262,28 @@ class B200ClassificationRBM:
         """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors.  With a process group
         ``input_data`` is this rank's shard of a minibatch of ``global_batch`` rows (default: shard x world)."""
         L = _lib.load()
-        x = self._pad_rows(input_data, self.num_visible)
-        B = x.shape[0]
+        B = len(input_data)
         if B < 2:
             raise ValueError("batch size must be >= 2 (the reference squeezes the batch axis at B = 1, :134)")
+        if self.pg is None and self.use_graphs:
+            C, lC = self.num_classes, _ld4(self.num_classes)
+
+            def launch(ent):
+                ws = self._ws
+                self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                           self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(),
+                           ent["x"].data_ptr(), ent["y"].data_ptr(), B, self.num_visible, self.num_hidden, C,
+                           float(self.learning_rate), float(factor), float(self.sparse_constant), ent["out"].data_ptr(),
+                           ent["pred"].data_ptr(), ent["out"].data_ptr() + 4 * B * lC, ws.data_ptr(), ws.numel() * 4)
+
+            ent = self._graph_entry(("disc", B, float(self.learning_rate), float(factor), float(self.sparse_constant)), B, launch)
+            if ent is not None:
+                self._stage(ent, input_data, class_label, B)
+                ent["graph"].replay()
+                self._step += 1
+                out = ent["out"].clone()          # the static buffers are overwritten by the next step
+                return out[B * lC], ent["pred"].to(torch.int64), out[:B * lC].view(B, lC)[:, :C]
+        x = self._pad_rows(input_data, self.num_visible)
         y = self._labels(class_label, B)
         probs = _padded(B, self.num_classes, self.device)
         pred = torch.empty(B, dtype=torch.int32, device=self.device)
@@ -250,8 +312,30 @@ class B200ClassificationRBM:
     def cd1_training(self, input_data, class_label, global_batch=None):
         """One CD-1 step (k = 1) on a minibatch (or this rank's shard of it); parameters updated in place."""
         L = _lib.load()
+        B = len(input_data)
+        if self.pg is None and self.use_graphs:
+            if self._step_dev is None:
+                self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+            def launch(ent):
+                ws = self._ws
+                self._call(L.qbm_rbm_cd1_step_dev, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                           self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(),
+                           ent["x"].data_ptr(), ent["y"].data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes,
+                           float(self.learning_rate), float(self.sparse_constant), ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)),
+                           ctypes.c_uint(0), self._step_dev.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+                self._step_dev.add_(1)            # part of the graph: the next replay draws from the next streams
+
+            ent = self._graph_entry(("cd1", B, float(self.learning_rate), float(self.sparse_constant)), B, launch)
+            if ent is not None:
+                if self._step_dev_val != self._step:          # eager steps in between: resynchronise the device counter
+                    self._step_dev.fill_(self._step & 0x3FFFFFFF)
+                self._stage(ent, input_data, class_label, B)
+                ent["graph"].replay()
+                self._step += 1
+                self._step_dev_val = self._step
+                return
         v0 = self._pad_rows(input_data, self.num_visible)
-        B = v0.shape[0]
         y0 = self._labels(class_label, B)
         ws = self._workspace(B)
         # sharded minibatches draw from disjoint Philox streams: the step counter is offset by the rank
