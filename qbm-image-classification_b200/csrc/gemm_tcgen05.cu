@@ -88,7 +88,18 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-template <int BN>
+// Epilogue features.  FM = EPI_DYN: every feature is tested at run time (the generic instantiation: ~4700 instructions, of
+// which a launch executes a fraction -- at batch 256 the instruction fetches of that epilogue were a measurable part of the
+// launch).  Otherwise FM is the exact set of features of the call and the rest of the code does not exist.
+constexpr unsigned EPI_C = 1u, EPI_CT = 2u, EPI_S = 4u, EPI_ST = 8u, EPI_BIAS = 16u, EPI_TAB = 32u, EPI_CIN = 64u, EPI_ACT = 128u;
+constexpr unsigned EPI_DYN = 0xffffffffu;
+template <unsigned FM, unsigned BIT> __device__ __forceinline__ bool epi_has(bool dyn)
+{
+    if constexpr (FM == EPI_DYN) return dyn;
+    else return (FM & BIT) != 0u;
+}
+
+template <int BN, unsigned FM>
 __global__ void __launch_bounds__(128, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const EpiParams ep,
                  int M, int N, int K)
@@ -154,14 +165,18 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     // ---- epilogue: warp w reads TMEM lanes 32w..32w+31 (row m0 + 32w + lane), 32 columns at a time ----
+    const bool hasC = epi_has<FM, EPI_C>(ep.C != nullptr), hasCt = epi_has<FM, EPI_CT>(ep.Ct != nullptr);
+    const bool hasS = epi_has<FM, EPI_S>(ep.S != nullptr), hasSt = epi_has<FM, EPI_ST>(ep.St != nullptr);
+    const bool hasBias = epi_has<FM, EPI_BIAS>(ep.bias_n != nullptr), hasTab = epi_has<FM, EPI_TAB>(ep.rowtab != nullptr);
+    const bool hasCin = epi_has<FM, EPI_CIN>(ep.Cin != nullptr), hasAct = epi_has<FM, EPI_ACT>(ep.act == 1);
     const int m = m0 + warp * 32 + lane;
     const bool row_ok = m < M;
-    const float *tabrow = (ep.rowtab != nullptr && row_ok) ? ep.rowtab + (size_t)ep.ridx[m] * ep.ldtab : nullptr;
+    const float *tabrow = (hasTab && row_ok) ? ep.rowtab + (size_t)ep.ridx[m] * ep.ldtab : nullptr;
     const uint32_t k0 = (uint32_t)ep.seed, k1 = (uint32_t)(ep.seed >> 32);
     const uint32_t strm = ep.stream + (ep.step_dev != nullptr ? 4u * __ldg(ep.step_dev) : 0u);
-    const bool vecc = ep.C != nullptr && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
-    const bool vecs = ep.S != nullptr && (ep.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.S) & 15) == 0;
-    const bool vecin = ep.Cin != nullptr && (ep.ldcin & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.Cin) & 15) == 0;
+    const bool vecc = hasC && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.C) & 15) == 0;
+    const bool vecs = hasS && (ep.lds & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.S) & 15) == 0;
+    const bool vecin = hasCin && (ep.ldcin & 3) == 0 && (reinterpret_cast<uintptr_t>(ep.Cin) & 15) == 0;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
@@ -181,7 +196,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             Philox4 u4 = {0u, 0u, 0u, 0u};
-            if (ep.S != nullptr || ep.St != nullptr)
+            if (hasS || hasSt)
                 u4 = philox4x32_10((uint32_t)m, (uint32_t)((nb >> 2) + j4), strm, 0x52424Du, k0, k1);
             const uint32_t us[4] = {u4.x, u4.y, u4.z, u4.w};
             // a lane owns 4 consecutive columns of its row here: the row-major outputs (C, S) and Cin move as one
@@ -190,7 +205,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int nq = nb + j4 * 4;
             const bool full4 = row_ok && (nq + 3 < N);
             float cin4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (ep.Cin != nullptr && row_ok) {
+            if (hasCin && row_ok) {
                 if (full4 && vecin) {
                     const float4 t4 = *reinterpret_cast<const float4 *>(ep.Cin + (size_t)m * ep.ldcin + nq);
                     cin4[0] = t4.x; cin4[1] = t4.y; cin4[2] = t4.z; cin4[3] = t4.w;
@@ -206,17 +221,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int n = nq + jj;
                 float v = ep.alpha * __uint_as_float(r[j4 * 4 + jj]);
                 if (n < N) {
-                    if (ep.bias_n != nullptr) v += __ldg(ep.bias_n + n);
-                    if (tabrow != nullptr) v += __ldg(tabrow + n);
+                    if (hasBias) v += __ldg(ep.bias_n + n);
+                    if (hasTab && tabrow != nullptr) v += __ldg(tabrow + n);
                 }
-                if (ep.act == 1) v = sigmoidf_(v);
-                if (ep.Cin != nullptr) v += ep.beta * cin4[jj];
+                if (hasAct) v = sigmoidf_(v);
+                if (hasCin) v += ep.beta * cin4[jj];
                 v4[jj] = v;
                 // u in [0,1) with 24 bits; sample = 1 with probability v
                 s4v[jj] = ((float)(us[jj] >> 8) * 5.9604644775390625e-8f < v) ? 1.0f : 0.0f;
             }
             if (row_ok) {
-                if (ep.C != nullptr) {
+                if (hasC) {
                     if (full4 && vecc) *reinterpret_cast<float4 *>(ep.C + (size_t)m * ep.ldc + nq) = make_float4(v4[0], v4[1], v4[2], v4[3]);
                     else {
 #pragma unroll
@@ -224,7 +239,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (nq + jj < N) ep.C[(size_t)m * ep.ldc + nq + jj] = v4[jj];
                     }
                 }
-                if (ep.S != nullptr) {
+                if (hasS) {
                     if (full4 && vecs) *reinterpret_cast<float4 *>(ep.S + (size_t)m * ep.lds + nq) = make_float4(s4v[0], s4v[1], s4v[2], s4v[3]);
                     else {
 #pragma unroll
@@ -236,8 +251,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int jj = 0; jj < 4; ++jj) {
                     const int n = nq + jj;
                     if (n >= N) continue;
-                    if (ep.Ct != nullptr) ep.Ct[(size_t)n * ep.ldct + m] = v4[jj];
-                    if (ep.St != nullptr) ep.St[(size_t)n * ep.ldst + m] = s4v[jj];
+                    if (hasCt) ep.Ct[(size_t)n * ep.ldct + m] = v4[jj];
+                    if (hasSt) ep.St[(size_t)n * ep.ldst + m] = s4v[jj];
                 }
             }
         }
@@ -315,24 +330,43 @@ int qbm_gemm_tf32_launch(const float *A, long long lda, const float *B, long lon
     if (rc) return rc;
     const dim3 grid((unsigned)((N + bn - 1) / bn), (unsigned)mt);
     // the attribute belongs to the current device (a process may drive several), so it is set per launch
-    switch (bn) {
-        case 256:
-            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<256>()));
-            gemm_tf32_kernel<256><<<grid, 128, smem_bytes<256>(), st>>>(tmA, tmB, ep, M, N, K);
-            break;
-        case 128:
-            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<128>()));
-            gemm_tf32_kernel<128><<<grid, 128, smem_bytes<128>(), st>>>(tmA, tmB, ep, M, N, K);
-            break;
-        case 64:
-            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<64>()));
-            gemm_tf32_kernel<64><<<grid, 128, smem_bytes<64>(), st>>>(tmA, tmB, ep, M, N, K);
-            break;
-        default:
-            QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<32>()));
-            gemm_tf32_kernel<32><<<grid, 128, smem_bytes<32>(), st>>>(tmA, tmB, ep, M, N, K);
-            break;
+#define QBM_GEMM_LAUNCH(BN_, FM_)                                                                                              \
+    do {                                                                                                                       \
+        QBM_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN_, FM_>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                         smem_bytes<BN_>()));                                                                  \
+        gemm_tf32_kernel<BN_, FM_><<<grid, 128, smem_bytes<BN_>(), st>>>(tmA, tmB, ep, M, N, K);                               \
+    } while (0)
+    if (bn >= 128) {
+        if (bn == 256) QBM_GEMM_LAUNCH(256, EPI_DYN);
+        else QBM_GEMM_LAUNCH(128, EPI_DYN);
+    } else {
+        // small problems (the training steps at batch 256): the feature sets the RBM steps use have their own instantiation
+        const unsigned fm = (ep.C ? EPI_C : 0u) | (ep.Ct ? EPI_CT : 0u) | (ep.S ? EPI_S : 0u) | (ep.St ? EPI_ST : 0u) |
+                            (ep.bias_n ? EPI_BIAS : 0u) | (ep.rowtab ? EPI_TAB : 0u) | (ep.Cin ? EPI_CIN : 0u) |
+                            (ep.act == 1 ? EPI_ACT : 0u);
+#define QBM_GEMM_CASE(FM_)                                                                                                     \
+    case (FM_):                                                                                                                \
+        if (bn == 64) QBM_GEMM_LAUNCH(64, (FM_));                                                                              \
+        else QBM_GEMM_LAUNCH(32, (FM_));                                                                                       \
+        break;
+        switch (fm) {
+            QBM_GEMM_CASE(EPI_C | EPI_BIAS)                                              // x.W + b_h
+            QBM_GEMM_CASE(EPI_C | EPI_CIN | EPI_CT)                                      // W += s x^T.D, W^T
+            QBM_GEMM_CASE(EPI_C | EPI_CIN)                                               // accumulate
+            QBM_GEMM_CASE(EPI_C)                                                         // gradient
+            QBM_GEMM_CASE(EPI_C | EPI_CT | EPI_S | EPI_BIAS | EPI_TAB | EPI_ACT)         // CD-1: ph0, ph0^T, h0
+            QBM_GEMM_CASE(EPI_S | EPI_ST | EPI_BIAS | EPI_ACT)                           // CD-1: v1, v1^T
+            QBM_GEMM_CASE(EPI_CT | EPI_BIAS | EPI_TAB | EPI_ACT)                         // CD-1: ph1^T
+            QBM_GEMM_CASE(EPI_C | EPI_BIAS | EPI_TAB | EPI_ACT)                          // sample_hidden
+            QBM_GEMM_CASE(EPI_C | EPI_BIAS | EPI_ACT)                                    // sample_visible
+            default:
+                if (bn == 64) QBM_GEMM_LAUNCH(64, EPI_DYN);
+                else QBM_GEMM_LAUNCH(32, EPI_DYN);
+                break;
+        }
+#undef QBM_GEMM_CASE
     }
+#undef QBM_GEMM_LAUNCH
     QBM_LAUNCH_OK("gemm_tf32_kernel");
     return QBM_OK;
 }

@@ -15,34 +15,22 @@ __device__ __forceinline__ float softplus(float z) { return fmaxf(z, 0.0f) + log
 
 constexpr int MAXC = 32;
 
-// out[c][r] = in[r][c]
-__global__ void transpose_kernel(const float *__restrict__ in, long long ldi, float *__restrict__ out, long long ldo,
-                                 int rows, int cols)
-{
-    __shared__ float tile[32][33];
-    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int r = r0 + i, c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (r < rows && c < cols) ? in[(size_t)r * ldi + c] : 0.0f;
-    }
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-        const int c = c0 + i, r = r0 + threadIdx.x;
-        if (c < cols && r < rows) out[(size_t)c * ldo + r] = tile[threadIdx.x][i];
-    }
-}
-
 // p(y|x) per row (ClassificationRBM.py:62-86) and, when Dt != null, the phase difference
 // D[b,h] = o[b,h,y_b] - sum_c p[b,c] o[b,h,c]  with o = sigmoid(A[b,h] + U[c,h])   (:106-128), stored transposed.
+// With xin / xt the block also writes row b of the minibatch as column b of x^T (the K-major operand of the W gradient).
 __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ U,
                                                       long long ldu, const float *__restrict__ b_c, const int *__restrict__ y,
                                                       int H, int C, float *__restrict__ P, long long ldp,
-                                                      float *__restrict__ Dt, long long lddt)
+                                                      float *__restrict__ Dt, long long lddt,
+                                                      const float *__restrict__ xin = nullptr, long long ldx = 0, int V = 0,
+                                                      float *__restrict__ xt = nullptr, long long ldxt = 0)
 {
     __shared__ float red[MAXC][8];
     __shared__ float prob[MAXC];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *Ab = A + (size_t)b * lda;
+    if (xt != nullptr)
+        for (int v = tid; v < V; v += 256) xt[(size_t)v * ldxt + b] = xin[(size_t)b * ldx + v];
     float sp[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) sp[c] = 0.0f;
@@ -62,16 +50,21 @@ __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__
         }
     }
     __syncthreads();
-    if (tid == 0) {
-        float s[MAXC], mx = -INFINITY;
-        for (int c = 0; c < C; ++c) {
-            float v = b_c[c];
-            for (int w = 0; w < 8; ++w) v += red[c][w];
-            s[c] = v; mx = fmaxf(mx, v);
+    if (warp == 0) {
+        // softmax over the classes, lane = class; sums in the fixed order of the serial loop they replace
+        float v = -INFINITY;
+        if (lane < C) {
+            v = b_c[lane];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) v += red[lane][w];
         }
+        float mx = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = lane < C ? __expf(v - mx) : 0.0f;
         float z = 0.0f;
-        for (int c = 0; c < C; ++c) { s[c] = __expf(s[c] - mx); z += s[c]; }
-        for (int c = 0; c < C; ++c) { prob[c] = s[c] / z; P[(size_t)b * ldp + c] = prob[c]; }
+        for (int c = 0; c < C; ++c) z += __shfl_sync(0xffffffffu, e, c);
+        if (lane < C) { prob[lane] = e / z; P[(size_t)b * ldp + lane] = e / z; }
     }
     if (Dt == nullptr) return;
     __syncthreads();
@@ -91,14 +84,59 @@ __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__
     }
 }
 
+// class-bias update, visible-bias decay, loss (CrossEntropyLoss applied to probabilities, :142) and argmax: one block
+__device__ __forceinline__ void rbm_disc_finish(float *__restrict__ b_c, float *__restrict__ b_v, const float *__restrict__ P,
+                                                long long ldp, const int *__restrict__ y, int B, int C, int V, float scale,
+                                                float sparse, int *__restrict__ pred, float *__restrict__ loss, int update,
+                                                float *__restrict__ gbc)
+{
+    __shared__ float redl[256];
+    const int tid = threadIdx.x;
+    float l = 0.0f;
+    for (int b = tid; b < B; b += blockDim.x) {
+        const float *p = P + (size_t)b * ldp;
+        float z = 0.0f, best = -1.0f; int arg = 0;
+        for (int c = 0; c < C; ++c) { z += __expf(p[c]); if (p[c] > best) { best = p[c]; arg = c; } }
+        l += __logf(z) - p[y[b]];
+        if (pred != nullptr) pred[b] = arg;
+    }
+    redl[tid] = l;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (tid < o) redl[tid] += redl[tid + o]; __syncthreads(); }
+    if (tid == 0 && loss != nullptr) loss[0] = (update == 2) ? redl[0] : redl[0] / (float)B;     // gradient mode: the sum
+    if (!update) return;
+    // class-bias gradient: warp w sums class w, w + 8, ... over the batch (lanes stride over b, fixed shuffle tree)
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int c = warp; c < C; c += 8) {
+        float g = 0.0f;
+        for (int b = lane; b < B; b += 32) g += (y[b] == c ? 1.0f : 0.0f) - P[(size_t)b * ldp + c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+        if (lane == 0) {
+            if (update == 2) gbc[c] = g;
+            else b_c[c] = b_c[c] + scale * g - sparse;
+        }
+    }
+    if (update != 2 && sparse != 0.0f)
+        for (int v = tid; v < V; v += blockDim.x) b_v[v] -= sparse;
+}
+
 // class-weight / hidden-bias gradients of the discriminative step and their SGD update (:88-99,120-136).
-// Block = 32 hidden units x 8 batch slices; the slices are combined in a fixed order (deterministic).
+// Block = 32 hidden units x 8 batch slices; the slices are combined in a fixed order (deterministic).  The grid has one
+// extra row of blocks (blockIdx.y == C) whose first block does the O(B C) rest of the step (rbm_disc_finish).
 __global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U,
                                                              long long ldu, float *__restrict__ b_h, const float *__restrict__ P,
                                                              long long ldp, const int *__restrict__ y, const float *__restrict__ Dt,
                                                              long long lddt, int B, int H, float scale, float sparse,
-                                                             float *__restrict__ gU, float *__restrict__ gbh)
+                                                             float *__restrict__ gU, float *__restrict__ gbh,
+                                                             int C, float *__restrict__ b_c, float *__restrict__ b_v, int V,
+                                                             int *__restrict__ pred, float *__restrict__ loss, int fin_update,
+                                                             float *__restrict__ gbc)
 {
+    if ((int)blockIdx.y == C) {
+        if (blockIdx.x == 0) rbm_disc_finish(b_c, b_v, P, ldp, y, B, C, V, scale, sparse, pred, loss, fin_update, gbc);
+        return;
+    }
     __shared__ float red[2][8][33];
     const int hx = threadIdx.x & 31, sy = threadIdx.x >> 5;
     const int h = blockIdx.x * 32 + hx;
@@ -130,53 +168,19 @@ __global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__res
     }
 }
 
-// class-bias update, visible-bias decay, loss (CrossEntropyLoss applied to probabilities, :142) and argmax
-__global__ void rbm_disc_finish_kernel(float *__restrict__ b_c, float *__restrict__ b_v, const float *__restrict__ P,
-                                       long long ldp, const int *__restrict__ y, int B, int C, int V, float scale,
-                                       float sparse, int *__restrict__ pred, float *__restrict__ loss, int update,
-                                       float *__restrict__ gbc = nullptr)
-{
-    __shared__ float red[256];
-    const int tid = threadIdx.x;
-    float l = 0.0f;
-    for (int b = tid; b < B; b += blockDim.x) {
-        const float *p = P + (size_t)b * ldp;
-        float z = 0.0f, best = -1.0f; int arg = 0;
-        for (int c = 0; c < C; ++c) { z += __expf(p[c]); if (p[c] > best) { best = p[c]; arg = c; } }
-        l += __logf(z) - p[y[b]];
-        if (pred != nullptr) pred[b] = arg;
-    }
-    red[tid] = l;
-    __syncthreads();
-    for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-    if (tid == 0 && loss != nullptr) loss[0] = (update == 2) ? red[0] : red[0] / (float)B;     // gradient mode: the sum
-    if (!update) return;
-    if (update == 2) {
-        if (tid < C) {
-            float g = 0.0f;
-            for (int b = 0; b < B; ++b) g += (y[b] == tid ? 1.0f : 0.0f) - P[(size_t)b * ldp + tid];
-            gbc[tid] = g;
-        }
-        return;
-    }
-    if (tid < C) {
-        float g = 0.0f;
-        for (int b = 0; b < B; ++b) g += (y[b] == tid ? 1.0f : 0.0f) - P[(size_t)b * ldp + tid];
-        b_c[tid] = b_c[tid] + scale * g - sparse;
-    }
-    if (sparse != 0.0f)
-        for (int v = tid; v < V; v += blockDim.x) b_v[v] -= sparse;
-}
-
 // p(y|h) = exp(h.U^T + b_c) L1-normalised (:54-60) and, when y1 != null, a categorical sample of it
 __global__ void __launch_bounds__(128) rbm_class_kernel(const float *__restrict__ Hm, long long ldh, const float *__restrict__ U,
                                                        long long ldu, const float *__restrict__ b_c, int H, int C,
                                                        float *__restrict__ P, long long ldp, int *__restrict__ y1,
                                                        unsigned long long seed, unsigned int stream,
-                                                       const unsigned int *__restrict__ step_dev = nullptr)
+                                                       const unsigned int *__restrict__ step_dev = nullptr,
+                                                       const float *__restrict__ xin = nullptr, long long ldx = 0, int V = 0,
+                                                       float *__restrict__ xt = nullptr, long long ldxt = 0)
 {
     __shared__ float red[MAXC][4];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (xt != nullptr)          // row b of the minibatch as column b of v0^T (the K-major operand of the W gradient)
+        for (int v = tid; v < V; v += 128) xt[(size_t)v * ldxt + b] = xin[(size_t)b * ldx + v];
     float acc[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) acc[c] = 0.0f;
@@ -267,13 +271,6 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
         g = warp_sum(g);
         if (lane == 0) b_c[i] = grad_mode ? g : b_c[i] + scale * g - sparse;
     }
-}
-
-int transpose(const float *in, long long ldi, float *out, long long ldo, int rows, int cols, cudaStream_t st)
-{
-    transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, st>>>(in, ldi, out, ldo, rows, cols);
-    QBM_LAUNCH_OK("transpose_kernel");
-    return QBM_OK;
 }
 
 struct Ws {   // carve-up of the caller's workspace (floats)
@@ -466,15 +463,13 @@ extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b
     e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
     // p(y|x) and D^T
-    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB);
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB, x, lV, V, w.xt, lB);
     QBM_LAUNCH_OK("rbm_rows_kernel");
-    if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
-    // class weights / hidden bias (reads the pre-update A, U), then class bias, loss, argmax
-    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
-                                                                   sparse_constant, nullptr, nullptr);
+    // class weights / hidden bias (reads the pre-update A, U); the extra row of blocks: class bias, loss, argmax
+    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C + 1), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
+                                                                       sparse_constant, nullptr, nullptr, C, b_c, b_v, V, pred,
+                                                                       loss, 1, nullptr);
     QBM_LAUNCH_OK("rbm_disc_update_kernel");
-    rbm_disc_finish_kernel<<<1, 256, 0, st>>>(b_c, b_v, probs, lC, y, B, C, V, scale, sparse_constant, pred, loss, 1);
-    QBM_LAUNCH_OK("rbm_disc_finish_kernel");
     // W += scale * x^T.D   (SGD update fused into the GEMM epilogue, which also writes the K-major copy W^T)
     EpiParams e2 = {};
     e2.C = W; e2.ldc = lH; e2.Cin = W; e2.ldcin = lH; e2.alpha = scale; e2.beta = 1.0f; e2.Ct = Wt; e2.ldct = lV;
@@ -506,12 +501,11 @@ static int cd1_step_impl(float *W, float *Wt, float *U, float *b_v, float *b_h, 
     e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
     e2.stream = step * 4u + 1u; e2.step_dev = step_dev;
     if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
-    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, step_dev);
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, step_dev, v0, lV, V, w.xt, lB);
     QBM_LAUNCH_OK("rbm_class_kernel");
     EpiParams e3 = {};
     e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
     if (int rc = qbm_gemm_tf32_launch(w.v1, lV, Wt, lV, B, H, V, e3, st)) return rc;
-    if (int rc = transpose(v0, lV, w.xt, lB, B, V, st)) return rc;
     // small parameters, then W += scale (v0^T ph0 - v1^T ph1) fused into two GEMM epilogues, then W^T
     const int mx = (V > H ? V : H) > C ? (V > H ? V : H) : C;
     rbm_cd_small_update_kernel<<<(mx + 7) / 8, 256, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, U, lH, b_v, b_h,
@@ -569,14 +563,12 @@ extern "C" QBM_API int qbm_rbm_disc_grad(const float *Wt, const float *U, const 
     EpiParams e1 = {};
     e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
-    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB);
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB, x, lV, V, w.xt, lB);
     QBM_LAUNCH_OK("rbm_rows_kernel");
-    if (int rc = transpose(x, lV, w.xt, lB, B, V, st)) return rc;
-    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C), 256, 0, st>>>(w.A, lH, const_cast<float *>(U), lH, nullptr, probs, lC, y, w.Dt,
-                                                                   lB, B, H, 0.0f, 0.0f, g.gU, g.gbh);
+    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C + 1), 256, 0, st>>>(w.A, lH, const_cast<float *>(U), lH, nullptr, probs, lC, y,
+                                                                       w.Dt, lB, B, H, 0.0f, 0.0f, g.gU, g.gbh, C, nullptr, nullptr,
+                                                                       V, pred, g.loss, 2, g.gbc);
     QBM_LAUNCH_OK("rbm_disc_update_kernel");
-    rbm_disc_finish_kernel<<<1, 256, 0, st>>>(nullptr, nullptr, probs, lC, y, B, C, V, 0.0f, 0.0f, pred, g.loss, 2, g.gbc);
-    QBM_LAUNCH_OK("rbm_disc_finish_kernel");
     QBM_CUDA_OK(cudaMemsetAsync(g.gbv, 0, (size_t)V * sizeof(float), st));        // the discriminative gradient has no b_v term (:138)
     EpiParams e2 = {};
     e2.C = g.gW; e2.ldc = lH; e2.alpha = 1.0f;
@@ -605,12 +597,11 @@ extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const f
     e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
     e2.stream = step * 4u + 1u;
     if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
-    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u);
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, nullptr, v0, lV, V, w.xt, lB);
     QBM_LAUNCH_OK("rbm_class_kernel");
     EpiParams e3 = {};
     e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
     if (int rc = qbm_gemm_tf32_launch(w.v1, lV, Wt, lV, B, H, V, e3, st)) return rc;
-    if (int rc = transpose(v0, lV, w.xt, lB, B, V, st)) return rc;
     const int mx = (V > H ? V : H) > C ? (V > H ? V : H) : C;
     rbm_cd_small_update_kernel<<<(mx + 7) / 8, 256, 0, st>>>(w.xt, w.v1t, lB, w.p0t, w.p1t, lB, y0, w.y1, g.gU, lH, g.gbv, g.gbh,
                                                                 g.gbc, B, V, H, C, 0.0f, 0.0f, 1);
