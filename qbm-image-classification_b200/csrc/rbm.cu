@@ -14,40 +14,32 @@ __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x
 __device__ __forceinline__ float softplus(float z) { return fmaxf(z, 0.0f) + log1pf(__expf(-fabsf(z))); }
 
 constexpr int MAXC = 32;
+constexpr int DSL = 8;      // batch slices of the fused discriminative gradient kernel
 
-// p(y|x) per row (ClassificationRBM.py:62-86) and, when Dt != null, the phase difference
-// D[b,h] = o[b,h,y_b] - sum_c p[b,c] o[b,h,c]  with o = sigmoid(A[b,h] + U[c,h])   (:106-128), stored transposed.
-// With xin / xt the block also writes row b of the minibatch as column b of x^T (the K-major operand of the W gradient).
+// p(y|x) per row (ClassificationRBM.py:62-86).  With xin / xt the block also writes row b of the minibatch as column b of x^T (the K-major operand of the W gradient).
 __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ U,
                                                       long long ldu, const float *__restrict__ b_c, const int *__restrict__ y,
                                                       int H, int C, float *__restrict__ P, long long ldp,
-                                                      float *__restrict__ Dt, long long lddt,
                                                       const float *__restrict__ xin = nullptr, long long ldx = 0, int V = 0,
-                                                      float *__restrict__ xt = nullptr, long long ldxt = 0)
+                                                      float *__restrict__ xt = nullptr, long long ldxt = 0,
+                                                      unsigned int *__restrict__ tick = nullptr, int nticks = 0)
 {
     __shared__ float red[MAXC][8];
-    __shared__ float prob[MAXC];
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float *Ab = A + (size_t)b * lda;
+    if (b == 0 && tick != nullptr)          // arrival counters of the gradient kernel that follows
+        for (int i = tid; i < nticks; i += 256) tick[i] = 0u;
     if (xt != nullptr)
         for (int v = tid; v < V; v += 256) xt[(size_t)v * ldxt + b] = xin[(size_t)b * ldx + v];
-    float sp[MAXC];
+    // class-outer loop: one scalar accumulator and ONE inlined softplus (a class-unrolled body is 32 copies of log1pf and
+    // spends the launch fetching instructions); the row of A stays in L1 across the classes
+    for (int c = 0; c < C; ++c) {
+        const float *Uc = U + (size_t)c * ldu;
+        float v = 0.0f;
+        for (int h = tid; h < H; h += 256) v += softplus(Ab[h] + __ldg(Uc + h));
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) sp[c] = 0.0f;
-    for (int h = tid; h < H; h += 256) {
-        const float a = Ab[h];
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-            if (c < C) sp[c] += softplus(a + __ldg(U + (size_t)c * ldu + h));
-    }
-#pragma unroll
-    for (int c = 0; c < MAXC; ++c) {
-        if (c < C) {
-            float v = sp[c];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[c][warp] = v;
-        }
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[c][warp] = v;
     }
     __syncthreads();
     if (warp == 0) {
@@ -64,23 +56,7 @@ __global__ void __launch_bounds__(256) rbm_rows_kernel(const float *__restrict__
         const float e = lane < C ? __expf(v - mx) : 0.0f;
         float z = 0.0f;
         for (int c = 0; c < C; ++c) z += __shfl_sync(0xffffffffu, e, c);
-        if (lane < C) { prob[lane] = e / z; P[(size_t)b * ldp + lane] = e / z; }
-    }
-    if (Dt == nullptr) return;
-    __syncthreads();
-    const int yb = y[b];
-    for (int h = tid; h < H; h += 256) {
-        const float a = Ab[h];
-        float pos = 0.0f, neg = 0.0f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            if (c < C) {
-                const float o = sigm(a + __ldg(U + (size_t)c * ldu + h));
-                neg += prob[c] * o;
-                if (c == yb) pos = o;
-            }
-        }
-        Dt[(size_t)h * lddt + b] = pos - neg;
+        if (lane < C) P[(size_t)b * ldp + lane] = e / z;
     }
 }
 
@@ -121,49 +97,110 @@ __device__ __forceinline__ void rbm_disc_finish(float *__restrict__ b_c, float *
         for (int v = tid; v < V; v += blockDim.x) b_v[v] -= sparse;
 }
 
-// class-weight / hidden-bias gradients of the discriminative step and their SGD update (:88-99,120-136).
-// Block = 32 hidden units x 8 batch slices; the slices are combined in a fixed order (deterministic).  The grid has one
-// extra row of blocks (blockIdx.y == C) whose first block does the O(B C) rest of the step (rbm_disc_finish).
-__global__ void __launch_bounds__(256) rbm_disc_update_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U,
-                                                             long long ldu, float *__restrict__ b_h, const float *__restrict__ P,
-                                                             long long ldp, const int *__restrict__ y, const float *__restrict__ Dt,
-                                                             long long lddt, int B, int H, float scale, float sparse,
-                                                             float *__restrict__ gU, float *__restrict__ gbh,
-                                                             int C, float *__restrict__ b_c, float *__restrict__ b_v, int V,
-                                                             int *__restrict__ pred, float *__restrict__ loss, int fin_update,
-                                                             float *__restrict__ gbc)
+// The O(B H C) part of the discriminative step after p(y|x) (:106-136, :88-99): the phase difference
+//   D[b,h] = o[b,h,y_b] - sum_c p[b,c] o[b,h,c],  o = sigmoid(A[b,h] + U[c,h])           (stored transposed: K-major for x^T.D)
+// and the class-weight / hidden-bias gradients  dU[c,h] = sum_b (1[y_b = c] - p[b,c]) o[b,h,c],  db_h[h] = sum_b D[b,h],
+// every sigmoid evaluated once.  Grid (h-tiles of 32, DSL batch slices + 1): a block sums its slice (warps over rows, lanes
+// over h, rows and warps combined in a fixed order), writes the partial sums, and the last block of an h-tile to arrive adds
+// the DSL partials in slice order and applies the update -- deterministic whichever block that is.  The extra row of
+// blocks (blockIdx.y == DSL) does the O(B C) rest of the step (rbm_disc_finish).
+__global__ void __launch_bounds__(256) rbm_disc_grad_kernel(const float *__restrict__ A, long long lda, float *__restrict__ U,
+                                                           long long ldu, float *__restrict__ b_h, const float *__restrict__ P,
+                                                           long long ldp, const int *__restrict__ y, float *__restrict__ Dt,
+                                                           long long lddt, int B, int H, int C, float scale, float sparse,
+                                                           float *__restrict__ gU, float *__restrict__ gbh,
+                                                           float *__restrict__ part, unsigned int *__restrict__ tick,
+                                                           float *__restrict__ b_c, float *__restrict__ b_v, int V,
+                                                           int *__restrict__ pred, float *__restrict__ loss, int fin_update,
+                                                           float *__restrict__ gbc)
 {
-    if ((int)blockIdx.y == C) {
+    if ((int)blockIdx.y == DSL) {
         if (blockIdx.x == 0) rbm_disc_finish(b_c, b_v, P, ldp, y, B, C, V, scale, sparse, pred, loss, fin_update, gbc);
         return;
     }
-    __shared__ float red[2][8][33];
-    const int hx = threadIdx.x & 31, sy = threadIdx.x >> 5;
-    const int h = blockIdx.x * 32 + hx;
-    const int c = blockIdx.y;
+    __shared__ float red[MAXC + 1][8][32];
+    __shared__ float pr[32][MAXC];
+    __shared__ float dtile[32][33];
+    __shared__ int yr[32];
+    __shared__ unsigned int last;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ht = blockIdx.x, sl = blockIdx.y;
+    const int h = ht * 32 + lane;
     const bool ok = h < H;
-    const float u = ok ? U[(size_t)c * ldu + h] : 0.0f;
-    float g = 0.0f, gb = 0.0f;
-    if (ok) {
-        for (int b = sy; b < B; b += 8) {
-            const float o = sigm(A[(size_t)b * lda + h] + u);
-            g += (y[b] == c ? o : 0.0f) - P[(size_t)b * ldp + c] * o;
-            if (c == 0) gb += Dt[(size_t)h * lddt + b];
+    const long long lH = ldu;                                  // partial sums use the leading dimension of U
+    const int SB = (B + DSL - 1) / DSL;
+    const int bbeg = sl * SB, bend = min(B, bbeg + SB);
+    float u[MAXC], gu[MAXC], gb = 0.0f;
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) { u[c] = (ok && c < C) ? U[(size_t)c * ldu + h] : 0.0f; gu[c] = 0.0f; }
+    for (int bb = bbeg; bb < bend; bb += 32) {
+        __syncthreads();
+        for (int i = tid; i < 32 * C; i += 256) {
+            const int r = i / C, c = i - r * C;
+            pr[r][c] = (bb + r < bend) ? P[(size_t)(bb + r) * ldp + c] : 0.0f;
+        }
+        if (tid < 32) yr[tid] = (bb + tid < bend) ? y[bb + tid] : -1;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = w + 8 * k, b = bb + r;
+            float d = 0.0f;
+            if (ok && b < bend) {
+                const float a = A[(size_t)b * lda + h];
+                const int yb = yr[r];
+                float pos = 0.0f, neg = 0.0f;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) {
+                    if (c < C) {
+                        const float o = sigm(a + u[c]);
+                        const float p = pr[r][c];
+                        neg += p * o;
+                        if (c == yb) pos = o;
+                        gu[c] += (c == yb ? o : 0.0f) - p * o;
+                    }
+                }
+                d = pos - neg;
+                gb += d;
+            }
+            dtile[r][lane] = d;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                          // transposed tile: lanes along the batch
+            const int hh = ht * 32 + w + 8 * k, b = bb + lane;
+            if (hh < H && b < bend) Dt[(size_t)hh * lddt + b] = dtile[lane][w + 8 * k];
         }
     }
-    red[0][sy][hx] = g;
-    red[1][sy][hx] = gb;
-    __syncthreads();
-    if (sy == 0 && ok) {
-        float gs = 0.0f, gbs = 0.0f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { gs += red[0][k][hx]; gbs += red[1][k][hx]; }
-        if (gU != nullptr) {                      // gradient mode (data-parallel steps): the raw sums, parameters untouched
-            gU[(size_t)c * ldu + h] = gs;
-            if (c == 0) gbh[h] = gbs;
+    for (int c = 0; c < MAXC; ++c)
+        if (c < C) red[c][w][lane] = gu[c];
+    red[C][w][lane] = gb;
+    __syncthreads();
+    for (int i = tid; i < (C + 1) * 32; i += 256) {
+        const int c = i >> 5, hx = i & 31;
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += red[c][k][hx];
+        if (ht * 32 + hx < H) part[((size_t)sl * (MAXC + 1) + c) * lH + ht * 32 + hx] = sum;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last = (atomicAdd(tick + ht, 1u) == (unsigned)(DSL - 1)) ? 1u : 0u;
+    __syncthreads();
+    if (last == 0u) return;
+    __threadfence();
+    for (int i = tid; i < (C + 1) * 32; i += 256) {
+        const int c = i >> 5, hh = ht * 32 + (i & 31);
+        if (hh >= H) continue;
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < DSL; ++k) sum += __ldcg(part + ((size_t)k * (MAXC + 1) + c) * lH + hh);
+        if (c < C) {
+            if (gU != nullptr) gU[(size_t)c * ldu + hh] = sum;             // gradient mode (data-parallel steps): the raw sums
+            else U[(size_t)c * ldu + hh] = U[(size_t)c * ldu + hh] + scale * sum;
         } else {
-            U[(size_t)c * ldu + h] = u + scale * gs;
-            if (c == 0) b_h[h] = b_h[h] + scale * gbs - sparse;
+            if (gU != nullptr) gbh[hh] = sum;
+            else b_h[hh] = b_h[hh] + scale * sum - sparse;
         }
     }
 }
@@ -276,13 +313,16 @@ __global__ void __launch_bounds__(256) rbm_cd_small_update_kernel(const float *_
 struct Ws {   // carve-up of the caller's workspace (floats)
     float *A, *P, *Dt, *xt, *p0, *p0t, *h0, *v1, *v1t, *p1t, *pc;
     int *y1;
+    float *part;             // [DSL][MAXC + 1][ld4(H)] per-slice partial sums of the discriminative gradients
+    unsigned int *tick;      // [(H + 31) / 32] arrival counters of the slices of an h-tile
 };
 
 size_t ws_floats(int B, int V, int H, int C)
 {
     const size_t lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
     // A[B,lH] P[B,lC] Dt[H,lB] xt[V,lB] p0[B,lH] p0t[H,lB] h0[B,lH] v1[B,lV] v1t[V,lB] p1t[H,lB] pc[B,lC] y1[B]
-    return (size_t)B * lH * 3 + (size_t)B * lC * 2 + (size_t)H * lB * 3 + (size_t)V * lB * 2 + (size_t)B * lV + lB + 64;
+    return (size_t)B * lH * 3 + (size_t)B * lC * 2 + (size_t)H * lB * 3 + (size_t)V * lB * 2 + (size_t)B * lV + lB + 64 +
+           (size_t)DSL * (MAXC + 1) * lH + (((size_t)H + 31) / 32 + 3) / 4 * 4;
 }
 
 Ws carve(void *workspace, int B, int V, int H, int C)
@@ -295,6 +335,8 @@ Ws carve(void *workspace, int B, int V, int H, int C)
     w.p0 = take((size_t)B * lH); w.p0t = take((size_t)H * lB); w.h0 = take((size_t)B * lH); w.v1 = take((size_t)B * lV);
     w.v1t = take((size_t)V * lB); w.p1t = take((size_t)H * lB); w.pc = take((size_t)B * lC);
     w.y1 = reinterpret_cast<int *>(take(lB));
+    w.part = take((size_t)DSL * (MAXC + 1) * lH);
+    w.tick = reinterpret_cast<unsigned int *>(take(((size_t)H + 31) / 32));
     return w;
 }
 
@@ -438,7 +480,7 @@ extern "C" QBM_API int qbm_rbm_class_given_x(const float *Wt, const float *U, co
     EpiParams ep = {};
     ep.C = w.A; ep.ldc = ld4(H); ep.bias_n = b_h; ep.alpha = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(x, ld4(V), Wt, ld4(V), B, H, V, ep, st)) return rc;
-    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, ld4(H), U, ld4(H), b_c, nullptr, H, C, P, ld4(C), nullptr, 0);
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, ld4(H), U, ld4(H), b_c, nullptr, H, C, P, ld4(C));
     QBM_LAUNCH_OK("rbm_rows_kernel");
     return QBM_OK;
 }
@@ -463,13 +505,14 @@ extern "C" QBM_API int qbm_rbm_disc_step(float *W, float *Wt, float *U, float *b
     e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
     // p(y|x) and D^T
-    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB, x, lV, V, w.xt, lB);
+    const int nht = (H + 31) / 32;
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, x, lV, V, w.xt, lB, w.tick, nht);
     QBM_LAUNCH_OK("rbm_rows_kernel");
-    // class weights / hidden bias (reads the pre-update A, U); the extra row of blocks: class bias, loss, argmax
-    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C + 1), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, scale,
-                                                                       sparse_constant, nullptr, nullptr, C, b_c, b_v, V, pred,
-                                                                       loss, 1, nullptr);
-    QBM_LAUNCH_OK("rbm_disc_update_kernel");
+    // D^T, class weights / hidden bias (reads the pre-update A, U); the extra row of blocks: class bias, loss, argmax
+    rbm_disc_grad_kernel<<<dim3(nht, DSL + 1), 256, 0, st>>>(w.A, lH, U, lH, b_h, probs, lC, y, w.Dt, lB, B, H, C, scale,
+                                                             sparse_constant, nullptr, nullptr, w.part, w.tick, b_c, b_v, V,
+                                                             pred, loss, 1, nullptr);
+    QBM_LAUNCH_OK("rbm_disc_grad_kernel");
     // W += scale * x^T.D   (SGD update fused into the GEMM epilogue, which also writes the K-major copy W^T)
     EpiParams e2 = {};
     e2.C = W; e2.ldc = lH; e2.Cin = W; e2.ldcin = lH; e2.alpha = scale; e2.beta = 1.0f; e2.Ct = Wt; e2.ldct = lV;
@@ -563,12 +606,13 @@ extern "C" QBM_API int qbm_rbm_disc_grad(const float *Wt, const float *U, const 
     EpiParams e1 = {};
     e1.C = w.A; e1.ldc = lH; e1.bias_n = b_h; e1.alpha = 1.0f;
     if (int rc = qbm_gemm_tf32_launch(x, lV, Wt, lV, B, H, V, e1, st)) return rc;
-    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, w.Dt, lB, x, lV, V, w.xt, lB);
+    const int nht = (H + 31) / 32;
+    rbm_rows_kernel<<<B, 256, 0, st>>>(w.A, lH, U, lH, b_c, y, H, C, probs, lC, x, lV, V, w.xt, lB, w.tick, nht);
     QBM_LAUNCH_OK("rbm_rows_kernel");
-    rbm_disc_update_kernel<<<dim3((H + 31) / 32, C + 1), 256, 0, st>>>(w.A, lH, const_cast<float *>(U), lH, nullptr, probs, lC, y,
-                                                                       w.Dt, lB, B, H, 0.0f, 0.0f, g.gU, g.gbh, C, nullptr, nullptr,
-                                                                       V, pred, g.loss, 2, g.gbc);
-    QBM_LAUNCH_OK("rbm_disc_update_kernel");
+    rbm_disc_grad_kernel<<<dim3(nht, DSL + 1), 256, 0, st>>>(w.A, lH, const_cast<float *>(U), lH, nullptr, probs, lC, y, w.Dt, lB,
+                                                             B, H, C, 0.0f, 0.0f, g.gU, g.gbh, w.part, w.tick, nullptr, nullptr,
+                                                             V, pred, g.loss, 2, g.gbc);
+    QBM_LAUNCH_OK("rbm_disc_grad_kernel");
     QBM_CUDA_OK(cudaMemsetAsync(g.gbv, 0, (size_t)V * sizeof(float), st));        // the discriminative gradient has no b_v term (:138)
     EpiParams e2 = {};
     e2.C = g.gW; e2.ldc = lH; e2.alpha = 1.0f;

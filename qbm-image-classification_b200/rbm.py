@@ -74,7 +74,6 @@ class B200ClassificationRBM:
         self.hidden_bias = torch.zeros(H, device=self.device)
         self.class_bias = torch.zeros(C, device=self.device)
         self._ws = None
-        self._ws_key = None
         self._grad = None
         self._step = 0
         # single-GPU training steps are a fixed sequence of ~7-10 small launches: from the second step of a given shape on
@@ -119,13 +118,13 @@ class B200ClassificationRBM:
 
     # ---- helpers ------------------------------------------------------------------------------------
     def _workspace(self, B):
-        key = B
-        if self._ws_key != key:
-            self._graphs.clear()                # captured steps point into the old workspace
-            L = _lib.load()
-            nbytes = L.qbm_rbm_workspace_bytes(B, self.num_visible, self.num_hidden, self.num_classes)
+        """Caller-owned workspace of the step functions; grows, never shrinks (captured steps point into it, so a new
+        allocation drops them)."""
+        L = _lib.load()
+        nbytes = L.qbm_rbm_workspace_bytes(B, self.num_visible, self.num_hidden, self.num_classes)
+        if self._ws is None or self._ws.numel() * 4 < nbytes:
+            self._graphs.clear()
             self._ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=self.device)
-            self._ws_key = key
         return self._ws
 
     def _pad_rows(self, x, cols):

@@ -297,3 +297,35 @@ def test_train_rbm_epoch_loop(qbm, cuda):
     assert nlls[-1] < nlls[0] and m.acc_per_epoch_list[-1] > 0.8
     with pytest.raises(NotImplementedError):
         m.train_rbm(loader, 1, method="generative")
+
+
+@pytest.mark.parametrize("mode", ["disc", "cd1"])
+def test_rbm_graph_replay_equals_eager_launches(qbm, cuda, mode):
+    """From the second step of a shape on, the single-GPU steps are replayed as one CUDA graph (static buffers, CD-1 step
+    counter on the device): the same kernels on the same inputs, so parameters and outputs are bit-identical to the eager
+    launches -- also across a change of batch size and back, and when a bias tensor is re-assigned in between."""
+    rng = np.random.default_rng(5)
+    V, H, C = 96, 40, 5
+    ms = [qbm.B200ClassificationRBM(V, H, k=1, num_classes=C, learning_rate=0.05, sparse_constant=0.001, seed=11,
+                                    device=cuda, use_graphs=ug) for ug in (False, True)]
+    sizes = [24, 24, 24, 10, 24, 10, 10, 24]
+    for step, B in enumerate(sizes):
+        x = (rng.random((B, V)) < 0.3).astype(np.float32)
+        y = rng.integers(0, C, B)
+        outs = []
+        for m in ms:
+            if step == 5:
+                m.hidden_bias = m.hidden_bias.clone()            # a new tensor: the captured pointers are stale
+            if mode == "disc":
+                loss, pred, probs = m.discriminative_training(torch.from_numpy(x).to(cuda), torch.from_numpy(y).to(cuda))
+                outs.append((loss.item(), pred.cpu().numpy(), probs.cpu().numpy()))
+            else:
+                m.cd1_training(x, y)
+        if mode == "disc":
+            assert outs[0][0] == outs[1][0] and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
+            assert outs[1][1].dtype == np.int64 and outs[1][2].shape == (B, C)
+        for a, b in zip((ms[0].weights, ms[0].class_weights, ms[0].visible_bias, ms[0].hidden_bias, ms[0].class_bias, ms[0]._Wt),
+                        (ms[1].weights, ms[1].class_weights, ms[1].visible_bias, ms[1].hidden_bias, ms[1].class_bias, ms[1]._Wt)):
+            assert torch.equal(a, b), f"step {step}"
+    assert any(isinstance(e, dict) for e in ms[1]._graphs.values()), "no step was captured"
+    assert not ms[0]._graphs
