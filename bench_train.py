@@ -135,6 +135,8 @@ def gpu_train_rate(cfg, qbm, torch, dev, world, rank, barrier, batch, steps, war
     e2e_s = time.perf_counter() - t0
     barrier()
     h2d = int(sl(X, 0).nbytes + sl(Y, 0).nbytes)
+    if hasattr(model, "release_graphs"):
+        model.release_graphs()                  # captured NCCL collectives must not outlive the process group
     return ms, e2e_s, h2d
 
 

@@ -194,6 +194,10 @@ int qbm_rbm_disc_grad(const float *Wt, const float *U, const float *b_h, const f
 int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h, const float *b_c,
                      const float *v0, const int *y0, int B, int V, int H, int C, unsigned long long seed, unsigned int step,
                      float *grad, void *workspace, size_t workspace_bytes, void *stream);
+/* qbm_rbm_cd1_grad with the step counter in device memory (see qbm_rbm_cd1_step_dev). */
+int qbm_rbm_cd1_grad_dev(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h, const float *b_c,
+                     const float *v0, const int *y0, int B, int V, int H, int C, unsigned long long seed, unsigned int step, const unsigned int *step_dev,
+                     float *grad, void *workspace, size_t workspace_bytes, void *stream);
 int qbm_rbm_apply_grad(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *grad, int V, int H,
                        int C, float scale, float sparse_constant, float *loss_out, float loss_scale, void *stream);
 

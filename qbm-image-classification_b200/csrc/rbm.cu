@@ -620,10 +620,10 @@ extern "C" QBM_API int qbm_rbm_disc_grad(const float *Wt, const float *U, const 
 }
 
 // CD-1 (the composition of :43-60) without R5: dW = v0^T ph0 - v1^T ph1, dU, db_v, db_h, db_c of this shard
-extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h,
-                                        const float *b_c, const float *v0, const int *y0, int B, int V, int H, int C,
-                                        unsigned long long seed, unsigned int step, float *grad, void *workspace,
-                                        size_t workspace_bytes, void *stream)
+static int cd1_grad_impl(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h,
+                         const float *b_c, const float *v0, const int *y0, int B, int V, int H, int C,
+                         unsigned long long seed, unsigned int step, const unsigned int *step_dev, float *grad,
+                         void *workspace, size_t workspace_bytes, void *stream)
 {
     if (int rc = check_dims("qbm_rbm_cd1_grad", B, V, H, C)) return rc;
     QBM_CHECK_ARG(W && Wt && U && b_v && b_h && b_c && v0 && y0 && grad && workspace, "qbm_rbm_cd1_grad: null pointer argument");
@@ -635,13 +635,13 @@ extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const f
     const long long lB = ld4(B), lV = ld4(V), lH = ld4(H), lC = ld4(C);
     EpiParams e = {};
     e.C = w.p0; e.ldc = lH; e.Ct = w.p0t; e.ldct = lB; e.S = w.h0; e.lds = lH; e.bias_n = b_h; e.rowtab = U; e.ridx = y0;
-    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u;
+    e.ldtab = lH; e.alpha = 1.0f; e.act = 1; e.seed = seed; e.stream = step * 4u + 0u; e.step_dev = step_dev;
     if (int rc = qbm_gemm_tf32_launch(v0, lV, Wt, lV, B, H, V, e, st)) return rc;
     EpiParams e2 = {};
     e2.S = w.v1; e2.lds = lV; e2.St = w.v1t; e2.ldst = lB; e2.bias_n = b_v; e2.alpha = 1.0f; e2.act = 1; e2.seed = seed;
-    e2.stream = step * 4u + 1u;
+    e2.stream = step * 4u + 1u; e2.step_dev = step_dev;
     if (int rc = qbm_gemm_tf32_launch(w.h0, lH, W, lH, B, V, H, e2, st)) return rc;
-    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, nullptr, v0, lV, V, w.xt, lB);
+    rbm_class_kernel<<<B, 128, 0, st>>>(w.h0, lH, U, lH, b_c, H, C, w.pc, lC, w.y1, seed, step * 4u + 2u, step_dev, v0, lV, V, w.xt, lB);
     QBM_LAUNCH_OK("rbm_class_kernel");
     EpiParams e3 = {};
     e3.Ct = w.p1t; e3.ldct = lB; e3.bias_n = b_h; e3.rowtab = U; e3.ridx = w.y1; e3.ldtab = lH; e3.alpha = 1.0f; e3.act = 1;
@@ -656,6 +656,24 @@ extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const f
     if (int rc = qbm_gemm_tf32_launch(w.xt, lB, w.p0t, lB, V, H, B, g1, st)) return rc;
     g1.Cin = g.gW; g1.ldcin = lH; g1.alpha = -1.0f; g1.beta = 1.0f;
     return qbm_gemm_tf32_launch(w.v1t, lB, w.p1t, lB, V, H, B, g1, st);
+}
+
+extern "C" QBM_API int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h,
+                                        const float *b_c, const float *v0, const int *y0, int B, int V, int H, int C,
+                                        unsigned long long seed, unsigned int step, float *grad, void *workspace,
+                                        size_t workspace_bytes, void *stream)
+{
+    return cd1_grad_impl(W, Wt, U, b_v, b_h, b_c, v0, y0, B, V, H, C, seed, step, nullptr, grad, workspace, workspace_bytes, stream);
+}
+
+// step counter in device memory (draws keyed by step + *step_dev), for CUDA-graph replays of the data-parallel step
+extern "C" QBM_API int qbm_rbm_cd1_grad_dev(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h,
+                                            const float *b_c, const float *v0, const int *y0, int B, int V, int H, int C,
+                                            unsigned long long seed, unsigned int step, const unsigned int *step_dev,
+                                            float *grad, void *workspace, size_t workspace_bytes, void *stream)
+{
+    QBM_CHECK_ARG(step_dev, "qbm_rbm_cd1_grad_dev: null step counter");
+    return cd1_grad_impl(W, Wt, U, b_v, b_h, b_c, v0, y0, B, V, H, C, seed, step, step_dev, grad, workspace, workspace_bytes, stream);
 }
 
 // R5 (:88-99) on the (all-reduced) gradient buffer: param += scale * grad with scale = factor * lr / global batch, the three

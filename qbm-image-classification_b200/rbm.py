@@ -14,12 +14,33 @@ Reference attributes ``weights [V,H]``, ``visible_bias [V]``, ``hidden_bias [H]`
 from __future__ import annotations
 
 import ctypes
+import weakref
 
 import numpy as np
 import torch
 
 from . import _lib
 from .sampler import _require_cuda, _stream_ptr
+
+
+# models that hold captured data-parallel steps: NCCL cannot destroy a communicator while CUDA graphs that captured its
+# collectives are alive, so torch.distributed.destroy_process_group is wrapped (once) to release them first
+_DP_GRAPH_MODELS = weakref.WeakSet()
+
+
+def _hook_destroy_process_group():
+    import torch.distributed as dist
+    if getattr(dist.destroy_process_group, "_qbm_b200_hook", False):
+        return
+    orig = dist.destroy_process_group
+
+    def destroy_process_group(group=None):
+        for m in list(_DP_GRAPH_MODELS):
+            m.release_graphs()
+        return orig(group)
+
+    destroy_process_group._qbm_b200_hook = True
+    dist.destroy_process_group = destroy_process_group
 
 
 def _ld4(c: int) -> int:
@@ -76,8 +97,9 @@ class B200ClassificationRBM:
         self._ws = None
         self._grad = None
         self._step = 0
-        # single-GPU training steps are a fixed sequence of ~7-10 small launches: from the second step of a given shape on
-        # they are replayed as one CUDA graph (static input / output buffers; the CD-1 step counter lives on the device)
+        # a training step is a fixed sequence of 4-9 small launches (plus the NCCL all-reduce of the data-parallel mode):
+        # from the second step of a given shape on it is replayed as one CUDA graph (static input / output buffers; the
+        # CD-1 step counter lives on the device)
         self.use_graphs = bool(use_graphs)
         self._graphs = {}
         self._step_dev = None
@@ -171,15 +193,7 @@ class B200ClassificationRBM:
             self._grad = torch.zeros(n, dtype=torch.float32, device=self.device)
         return self._grad
 
-    def _apply_grad(self, grad, global_batch, factor, loss):
-        """update_weights (:88-99) from the all-reduced gradient sums: one fused launch (W, W^T, U, the biases, the loss)."""
-        L = _lib.load()
-        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(),
-                   self.num_visible, self.num_hidden, self.num_classes, float(factor * self.learning_rate / global_batch),
-                   float(self.sparse_constant), loss.data_ptr() if loss is not None else None, float(1.0 / global_batch))
-
-    # ---- CUDA-graph replay of the single-GPU steps -----------------------------------------------------------------
+    # ---- CUDA-graph replay of the training steps -----------------------------------------------------------------
     def _graph_entry(self, key, B, launch):
         """None on the first step of a key (the caller runs it eagerly, which also warms the kernels up), afterwards the
         captured step: static buffers x [B, ld4(V)], y int32 [B], out = [probs (B x ld4(C)) | loss] and pred int32 [B]."""
@@ -195,6 +209,9 @@ class B200ClassificationRBM:
             ent = {"x": _padded(B, V, self.device), "y": torch.zeros(B, dtype=torch.int32, device=self.device),
                    "out": torch.zeros(B * _ld4(C) + 4, dtype=torch.float32, device=self.device),
                    "pred": torch.zeros(B, dtype=torch.int32, device=self.device)}
+            if self.pg is not None:
+                _DP_GRAPH_MODELS.add(self)
+                _hook_destroy_process_group()
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.device(self.device), torch.cuda.graph(g, capture_error_mode="thread_local"):
@@ -202,6 +219,12 @@ class B200ClassificationRBM:
             ent["graph"] = g
             self._graphs[key] = ent
         return ent
+
+    def release_graphs(self):
+        """Drop every captured step (they are re-captured on demand).  NCCL cannot tear a communicator down while CUDA graphs
+        that captured its collectives are alive: ``torch.distributed.destroy_process_group`` is wrapped to call this for every
+        live data-parallel model; call it yourself if you destroy the group some other way."""
+        self._graphs.clear()
 
     def _stage(self, ent, x, y, B):
         V = self.num_visible
@@ -257,25 +280,66 @@ class B200ClassificationRBM:
         return P[:, :self.num_classes]
 
     # ---- training steps -----------------------------------------------------------------------------------
+    def _seed64(self):
+        return ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1))
+
+    def _disc_launch(self, B, factor, gb, xp, yp, probs_p, pred_p, loss_p):
+        """All launches of one discriminative step on raw device pointers (run eagerly, or once under graph capture).
+        Data-parallel: the gradient sums of this shard into the flat buffer, ONE all-reduce, one fused apply."""
+        L = _lib.load()
+        ws = self._workspace(B)
+        V, H, C = self.num_visible, self.num_hidden, self.num_classes
+        if self.pg is None:
+            self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), xp, yp, B, V, H, C,
+                       float(self.learning_rate), float(factor), float(self.sparse_constant), probs_p, pred_p, loss_p,
+                       ws.data_ptr(), ws.numel() * 4)
+            return
+        import torch.distributed as dist
+        grad = self._grad_buffer()
+        self._call(L.qbm_rbm_disc_grad, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
+                   self.class_bias.data_ptr(), xp, yp, B, V, H, C, grad.data_ptr(), probs_p, pred_p, ws.data_ptr(), ws.numel() * 4)
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(), V, H, C,
+                   float(factor * self.learning_rate / gb), float(self.sparse_constant), loss_p, float(1.0 / gb))
+
+    def _cd1_launch(self, B, gb, xp, yp, step_host, step_dev_p):
+        """All launches of one CD-1 step; draws are keyed by step_host (+ the device counter when step_dev_p is given)."""
+        L = _lib.load()
+        ws = self._workspace(B)
+        V, H, C = self.num_visible, self.num_hidden, self.num_classes
+        params = (self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
+                  self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), xp, yp, B, V, H, C)
+        step = (ctypes.c_uint(step_host),) if step_dev_p is None else (ctypes.c_uint(step_host), step_dev_p)
+        if self.pg is None:
+            fn = L.qbm_rbm_cd1_step if step_dev_p is None else L.qbm_rbm_cd1_step_dev
+            self._call(fn, *params, float(self.learning_rate), float(self.sparse_constant), self._seed64(), *step,
+                       ws.data_ptr(), ws.numel() * 4)
+            return
+        import torch.distributed as dist
+        grad = self._grad_buffer()
+        fn = L.qbm_rbm_cd1_grad if step_dev_p is None else L.qbm_rbm_cd1_grad_dev
+        self._call(fn, *params, self._seed64(), *step, grad.data_ptr(), ws.data_ptr(), ws.numel() * 4)
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
+                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(), V, H, C,
+                   float(self.learning_rate / gb), float(self.sparse_constant), None, float(1.0 / gb))
+
     def discriminative_training(self, input_data, class_label, factor=1, global_batch=None):
         """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors.  With a process group
         ``input_data`` is this rank's shard of a minibatch of ``global_batch`` rows (default: shard x world)."""
-        L = _lib.load()
         B = len(input_data)
         if B < 2:
             raise ValueError("batch size must be >= 2 (the reference squeezes the batch axis at B = 1, :134)")
-        if self.pg is None and self.use_graphs:
-            C, lC = self.num_classes, _ld4(self.num_classes)
-
+        C, lC = self.num_classes, _ld4(self.num_classes)
+        gb = float(global_batch if global_batch is not None else B * self._world())
+        if self.use_graphs:
             def launch(ent):
-                ws = self._ws
-                self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                           self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(),
-                           ent["x"].data_ptr(), ent["y"].data_ptr(), B, self.num_visible, self.num_hidden, C,
-                           float(self.learning_rate), float(factor), float(self.sparse_constant), ent["out"].data_ptr(),
-                           ent["pred"].data_ptr(), ent["out"].data_ptr() + 4 * B * lC, ws.data_ptr(), ws.numel() * 4)
+                self._disc_launch(B, factor, gb, ent["x"].data_ptr(), ent["y"].data_ptr(), ent["out"].data_ptr(),
+                                  ent["pred"].data_ptr(), ent["out"].data_ptr() + 4 * B * lC)
 
-            ent = self._graph_entry(("disc", B, float(self.learning_rate), float(factor), float(self.sparse_constant)), B, launch)
+            ent = self._graph_entry(("disc", B, float(self.learning_rate), float(factor), float(self.sparse_constant), gb), B, launch)
             if ent is not None:
                 self._stage(ent, input_data, class_label, B)
                 ent["graph"].replay()
@@ -284,51 +348,31 @@ class B200ClassificationRBM:
                 return out[B * lC], ent["pred"].to(torch.int64), out[:B * lC].view(B, lC)[:, :C]
         x = self._pad_rows(input_data, self.num_visible)
         y = self._labels(class_label, B)
-        probs = _padded(B, self.num_classes, self.device)
+        probs = _padded(B, C, self.device)
         pred = torch.empty(B, dtype=torch.int32, device=self.device)
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        ws = self._workspace(B)
-
-        if self.pg is None:
-            self._call(L.qbm_rbm_disc_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), x.data_ptr(),
-                       y.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(self.learning_rate),
-                       float(factor), float(self.sparse_constant), probs.data_ptr(), pred.data_ptr(), loss.data_ptr(),
-                       ws.data_ptr(), ws.numel() * 4)
-        else:
-            # data-parallel minibatch: the gradient sums of this shard into the flat buffer, ONE all-reduce, one fused apply
-            import torch.distributed as dist
-            grad = self._grad_buffer()
-            self._call(L.qbm_rbm_disc_grad, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
-                       self.class_bias.data_ptr(), x.data_ptr(), y.data_ptr(), B, self.num_visible, self.num_hidden,
-                       self.num_classes, grad.data_ptr(), probs.data_ptr(), pred.data_ptr(), ws.data_ptr(), ws.numel() * 4)
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
-            gb = float(global_batch if global_batch is not None else B * self._world())
-            self._apply_grad(grad, gb, factor, loss)
+        self._disc_launch(B, factor, gb, x.data_ptr(), y.data_ptr(), probs.data_ptr(), pred.data_ptr(), loss.data_ptr())
         self._step += 1
-        return loss[0], pred.to(torch.int64), probs[:, :self.num_classes]
+        return loss[0], pred.to(torch.int64), probs[:, :C]
 
     def cd1_training(self, input_data, class_label, global_batch=None):
-        """One CD-1 step (k = 1) on a minibatch (or this rank's shard of it); parameters updated in place."""
-        L = _lib.load()
+        """One CD-1 step (k = 1) on a minibatch (or this rank's shard of it); parameters updated in place.  Sharded
+        minibatches draw from disjoint Philox streams: stream id = step * world + rank."""
         B = len(input_data)
-        if self.pg is None and self.use_graphs:
+        world, rank = self._world(), self._rank()
+        gb = float(global_batch if global_batch is not None else B * world)
+        if self.use_graphs:
             if self._step_dev is None:
                 self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
 
             def launch(ent):
-                ws = self._ws
-                self._call(L.qbm_rbm_cd1_step_dev, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                           self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(),
-                           ent["x"].data_ptr(), ent["y"].data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes,
-                           float(self.learning_rate), float(self.sparse_constant), ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)),
-                           ctypes.c_uint(0), self._step_dev.data_ptr(), ws.data_ptr(), ws.numel() * 4)
-                self._step_dev.add_(1)            # part of the graph: the next replay draws from the next streams
+                self._cd1_launch(B, gb, ent["x"].data_ptr(), ent["y"].data_ptr(), rank, self._step_dev.data_ptr())
+                self._step_dev.add_(world)        # part of the graph: the next replay draws from the next streams
 
-            ent = self._graph_entry(("cd1", B, float(self.learning_rate), float(self.sparse_constant)), B, launch)
+            ent = self._graph_entry(("cd1", B, float(self.learning_rate), float(self.sparse_constant), gb), B, launch)
             if ent is not None:
                 if self._step_dev_val != self._step:          # eager steps in between: resynchronise the device counter
-                    self._step_dev.fill_(self._step & 0x3FFFFFFF)
+                    self._step_dev.fill_((self._step * world) & 0x3FFFFFFF)
                 self._stage(ent, input_data, class_label, B)
                 ent["graph"].replay()
                 self._step += 1
@@ -336,27 +380,7 @@ class B200ClassificationRBM:
                 return
         v0 = self._pad_rows(input_data, self.num_visible)
         y0 = self._labels(class_label, B)
-        ws = self._workspace(B)
-        # sharded minibatches draw from disjoint Philox streams: the step counter is offset by the rank
-        stream = (self._step * self._world() + self._rank()) & 0x3FFFFFFF
-
-        if self.pg is None:
-            self._call(L.qbm_rbm_cd1_step, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(),
-                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes, float(self.learning_rate),
-                       float(self.sparse_constant), ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream),
-                       ws.data_ptr(), ws.numel() * 4)
-        else:
-            import torch.distributed as dist
-            grad = self._grad_buffer()
-            self._call(L.qbm_rbm_cd1_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                       self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), v0.data_ptr(),
-                       y0.data_ptr(), B, self.num_visible, self.num_hidden, self.num_classes,
-                       ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1)), ctypes.c_uint(stream), grad.data_ptr(), ws.data_ptr(),
-                       ws.numel() * 4)
-            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
-            gb = float(global_batch if global_batch is not None else B * self._world())
-            self._apply_grad(grad, gb, 1.0, None)
+        self._cd1_launch(B, gb, v0.data_ptr(), y0.data_ptr(), (self._step * world + rank) & 0x3FFFFFFF, None)
         self._step += 1
 
     def predict(self, input_data):

@@ -18,7 +18,9 @@ def _free_port():
 
 
 def _worker(rank, world, port, out_dir):
+    import faulthandler
     import sys
+    faulthandler.dump_traceback_later(150, exit=True)       # a rank stuck in a collective: show where, do not hang the box
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch.distributed as dist
     import qbm_b200
@@ -114,6 +116,32 @@ def _worker(rank, world, port, out_dir):
         got = torch.cat([(dp.weights - W0).reshape(-1), (dp.class_weights - U0).reshape(-1), (dp.visible_bias - bv0).reshape(-1)])
         res["rbm_cd1"] = float((got - deltas).abs().max())
         res["rbm_cd1_wt"] = float((dp._Wt[:, :784] - dp._W[:, :500].t()).abs().max())
+        # ---- several steps: from the second one on the data-parallel step (shard kernels + NCCL all-reduce + apply) is replayed
+        # as one CUDA graph; it must follow the eager launches (use_graphs=False) and, for the discriminative step, the
+        # single-GPU model on the whole minibatch
+        mkg = lambda pg_, ug: qbm_b200.B200ClassificationRBM(784, 500, 1, num_classes=10, learning_rate=0.05, seed=7, device=dev,
+                                                             process_group=pg_, use_graphs=ug)
+        single, dpg, dpe = mkg(None, True), mkg(pg, True), mkg(pg, False)
+        cg, ce = mkg(pg, True), mkg(pg, False)
+        d_disc = d_cd1 = d_single = 0.0
+        for step in range(4):
+            xs = (rng.random((64, 784)) < 0.3).astype(np.float32)
+            ys = rng.integers(0, 10, 64)
+            l0, _, _ = single.discriminative_training(xs, ys)
+            l1, _, p1 = dpg.discriminative_training(xs[lo:hi], ys[lo:hi], global_batch=64)
+            l2, _, p2 = dpe.discriminative_training(xs[lo:hi], ys[lo:hi], global_batch=64)
+            d_disc = max(d_disc, float((dpg.weights - dpe.weights).abs().max()), float((dpg.class_weights - dpe.class_weights).abs().max()),
+                         abs(float(l1) - float(l2)), float((p1 - p2).abs().max()))
+            d_single = max(d_single, float((dpg.weights - single.weights).abs().max()), abs(float(l1) - float(l0)))
+            cg.cd1_training(xs[lo:hi], ys[lo:hi], global_batch=64)
+            ce.cd1_training(xs[lo:hi], ys[lo:hi], global_batch=64)
+            d_cd1 = max(d_cd1, float((cg.weights - ce.weights).abs().max()), float((cg.class_weights - ce.class_weights).abs().max()),
+                        float((cg.visible_bias - ce.visible_bias).abs().max()))
+        res["rbm_graph_disc"], res["rbm_graph_cd1"], res["rbm_graph_vs_single"] = d_disc, d_cd1, d_single
+        res["rbm_graph_captured"] = 0.0 if any(isinstance(e, dict) for e in dpg._graphs.values()) and \
+            any(isinstance(e, dict) for e in cg._graphs.values()) else 1.0
+        for m in (single, dpg, dpe, cg, ce, dp, alone):
+            m.release_graphs()                  # captured NCCL collectives must go before the communicator does
         np.save(os.path.join(out_dir, f"rank{rank}.npy"), res, allow_pickle=True)
     finally:
         dist.destroy_process_group()
@@ -134,3 +162,6 @@ def test_two_gpu_data_parallel_equals_single_gpu(tmp_path):
         assert res["rbm"] < 2e-5, res            # float32 parameters, TF32 products
         assert res["sa"] == 0.0, res             # bit-identical reads
         assert res["sa_gather"] == 0.0, res      # sharded + all-gathered sample_Q == single-GPU sample_Q
+        # graph replays (incl. the captured all-reduce) == eager launches; 4 data-parallel steps == 4 single-GPU steps
+        assert res["rbm_graph_captured"] == 0.0 and res["rbm_graph_disc"] < 1e-6 and res["rbm_graph_cd1"] < 1e-6, res
+        assert res["rbm_graph_vs_single"] < 1e-4, res
