@@ -5,7 +5,8 @@ statistic (clamped - unclamped) plus the loss, then the identical SGD update on 
 The reference has no distributed layer (its only parallelism is a process pool of sampler calls,
 src/model/faster_dqbm.py:98-111,578-596); the sum-then-divide-by-the-global-batch order matches
 src/train/train.py:101-112 and src/model/faster_dqbm.py:1042-1049.  The functions here work on tensors
-of any device, so the same code runs under NCCL on GPUs and under gloo in the CPU tests.
+of any device, so the same code runs under NCCL on GPUs and under gloo in the CPU tests (the update itself is the
+native K9 `qbm_sgd_apply` on the flat parameter buffer).
 """
 from __future__ import annotations
 
@@ -21,25 +22,9 @@ def shard_range(total: int, world: int, rank: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < extra else 0)
 
 
-def pack(tensors) -> torch.Tensor:
-    """One flat float64 buffer from a list of tensors (row-major, in order)."""
-    return torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
-
-
 def all_reduce_sum_(flat: torch.Tensor, group=None) -> torch.Tensor:
     """In-place sum over the ranks of `group`; a no-op without a process group."""
     if group is not None:
         import torch.distributed as dist
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     return flat
-
-
-def sgd_apply_(params, flat: torch.Tensor, lr: float, global_batch: float) -> int:
-    """param -= lr * (err / global_batch) for consecutive slices of `flat` shaped like `params`;
-    returns the number of elements consumed."""
-    pos = 0
-    for p in params:
-        cnt = p.numel()
-        p -= lr * (flat[pos:pos + cnt].reshape(p.shape).to(p.dtype) / global_batch)
-        pos += cnt
-    return pos

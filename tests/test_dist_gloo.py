@@ -1,6 +1,7 @@
-"""CPU, world_size 2, gloo: the multi-GPU plumbing of the training steps (qbm_b200.dist) -- sharding of the
-minibatch, one all-reduce of the flat statistics buffer, identical SGD update on every rank -- gives the
-single-process result."""
+"""CPU, world_size 2, gloo: the multi-GPU plumbing of the training steps -- the product's `shard_range` and
+`all_reduce_sum_` (qbm_b200.dist) around a flat statistics buffer laid out like the trainers' error buffer
+[statistics..., loss], followed by the update K9 applies (`param -= lr * err / global_batch`, restated here in torch
+because K9 is CUDA) -- gives the single-process result on every rank."""
 import os
 import socket
 
@@ -15,6 +16,21 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def _pack(tensors):
+    """the trainers' flat float64 error buffer: every statistic row-major, in parameter order, the loss last"""
+    return torch.cat([t.reshape(-1).to(torch.float64) for t in tensors])
+
+
+def _sgd_apply(params, flat, lr, global_batch):
+    """K9 (csrc/disc_qbm.cu qbm_sgd_apply) restated: param -= lr * (err / global_batch) over consecutive slices"""
+    pos = 0
+    for p in params:
+        cnt = p.numel()
+        p -= lr * (flat[pos:pos + cnt].reshape(p.shape).to(p.dtype) / global_batch)
+        pos += cnt
+    return pos
 
 
 def _worker(rank, world, port, out_dir):
@@ -33,19 +49,19 @@ def _worker(rank, world, port, out_dir):
         params0 = [torch.from_numpy(rng.standard_normal(s)) for s in shapes]
         lo, hi = D.shard_range(B, world, rank)
         err = [sum(per_image[i][k] for i in range(lo, hi)) for k in range(len(shapes))]
-        flat = D.pack(err + [losses[lo:hi].sum()])
+        flat = _pack(err + [losses[lo:hi].sum()])
         D.all_reduce_sum_(flat, dist.group.WORLD)
         params = [p.clone() for p in params0]
-        used = D.sgd_apply_(params, flat, 0.3, float(B))
+        used = _sgd_apply(params, flat, 0.3, float(B))
         assert used == flat.numel() - 1
         # single-process reference
         ref = [p.clone() for p in params0]
-        full = D.pack([sum(per_image[i][k] for i in range(B)) for k in range(len(shapes))] + [losses.sum()])
-        D.sgd_apply_(ref, D.all_reduce_sum_(full, None), 0.3, float(B))
+        full = _pack([sum(per_image[i][k] for i in range(B)) for k in range(len(shapes))] + [losses.sum()])
+        _sgd_apply(ref, D.all_reduce_sum_(full, None), 0.3, float(B))
         ok = all(torch.allclose(a, b, rtol=0, atol=1e-13) for a, b in zip(params, ref))
         ok = ok and abs(float(flat[-1]) - float(losses.sum())) < 1e-12
         # every rank ends with the same parameters
-        chk = D.pack(params).clone()
+        chk = _pack(params).clone()
         gathered = [torch.zeros_like(chk) for _ in range(world)]
         dist.all_gather(gathered, chk)
         ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)

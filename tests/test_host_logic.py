@@ -119,3 +119,30 @@ def test_shim_install_and_neal_argument_checks(qbm):
     finally:
         qbm.shims.uninstall()
     assert "dimod" not in sys.modules and "neal" not in sys.modules
+
+
+def test_destroy_process_group_releases_captured_data_parallel_steps():
+    """NCCL cannot destroy a communicator while CUDA graphs that captured its collectives are alive: models with captured
+    data-parallel steps register themselves and torch.distributed.destroy_process_group is wrapped to release them first."""
+    import socket
+    import torch.distributed as dist
+    import qbm_b200.rbm as R
+
+    class Fake:
+        released = 0
+
+        def release_graphs(self):
+            self.released += 1
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        m = Fake()
+        R._DP_GRAPH_MODELS.add(m)
+        R._hook_destroy_process_group()
+        R._hook_destroy_process_group()          # idempotent
+    finally:
+        dist.destroy_process_group()
+    assert m.released == 1 and not dist.is_initialized()
