@@ -148,3 +148,22 @@ def test_convdeep_restricted_no_bias_and_float64_stats(qbm, cuda):
     assert np.array_equal(got["b_conv"], p0["b_conv"])              # 'none': never touched
     with pytest.raises(ValueError):
         qbm.ConvDeepQBM(144, 1, image_shape=(12, 12), pooling_type="probabilistic")
+
+
+@pytest.mark.parametrize("name,one_hot", [("convdeep_binary.npz", False), ("convdeep_onehot.npz", True), ("convdeep_c3.npz", False)])
+def test_run_unclamped_probabilities_from_the_reference_samples(qbm, cuda, name, one_hot):
+    """P1 (src/train/pipeline.py:24-36, RunOutputs.probs): the class probabilities the product derives from a sample set are
+    the reference's, checked directly on the reference's OWN unclamped sample sets (recorded in the golden fixture with the
+    probabilities run_unclamped returned for them) -- not only through the loss."""
+    g = np.load(os.path.join(G, name))
+    if "Su" not in g.files:
+        pytest.skip("fixture keeps digests of the sample sets only")
+    Su = g["Su"]
+    one_hot = bool(g["one_hot"]) if "one_hot" in g.files else one_hot
+    n_out = g["probs"].shape[1] if one_hot else 1
+    m = qbm.ConvDeepQBM.__new__(qbm.ConvDeepQBM)          # only the hidden / output split of the variable layout is needed
+    m.n_hidden = Su.shape[2] - n_out
+    mu, _ = qbm.phase_stats(torch.from_numpy(np.ascontiguousarray(Su)).to(cuda), second=False)
+    probs = m._probs(mu, one_hot).cpu().numpy()
+    assert probs.shape == g["probs"].shape
+    assert np.allclose(probs, g["probs"], rtol=0, atol=1e-6), np.abs(probs - g["probs"]).max()

@@ -304,3 +304,24 @@ def test_qubo_to_ising_device_matches_host(qbm, cuda):
     Z = torch.zeros((1, 3, 3), dtype=torch.float64, device=cuda)
     _, _, _, rz = qbm.qubo_to_ising_device(Z)
     assert rz.cpu().numpy().tolist() == [[0.0, 0.0]]
+
+
+@pytest.mark.parametrize("n,reads,sweeps", [(34, 16, 300), (193, 8, 200), (1100, 3, 60)])
+def test_trajectory_from_the_oracles_own_glue(qbm, oracle, cuda, n, reads, sweeps):
+    """The other trajectory tests prepare h, J and the schedule with the product's `qbm.ising`; here every input of the
+    kernel comes from the ORACLE's restatement of the dimod / neal glue (BINARY -> SPIN, legacy beta range, geometric
+    schedule: oracle.py), so a regression of the product's host logic on the GPU box cannot hide behind itself: the product's
+    whole host-buffer call (`sample_qubo_batch`: device-side conversion + schedule + kernels) must return the states the
+    replay oracle computes from the oracle's own inputs."""
+    Q = random_qubo(n, seed=91 + n)
+    h64, J64, offset, irow, icol, jval = oracle.qubo_to_ising(Q)
+    betas64, spb = oracle.beta_schedule(oracle.default_beta_range(h64, jval, irow, icol), sweeps)
+    J32 = np.ascontiguousarray(J64, dtype=np.float32)
+    h32 = np.ascontiguousarray(h64, dtype=np.float32)
+    b32 = np.ascontiguousarray(betas64, dtype=np.float32)
+    seed = 4242 + n
+    ref, _ = oracle.replay_sample(J32, h32, b32, spb, seed, 0, reads)
+    got, energies, info = qbm.sample_qubo_batch(Q, reads, sweeps, seed=seed, initial_states_generator="philox", device=cuda)
+    assert np.array_equal(got[0], ref)
+    assert np.allclose(energies[0], oracle.qubo_energies(Q, ref), rtol=1e-12, atol=1e-9)
+    assert abs(float(np.ravel(info["offset"])[0]) - float(offset)) <= 1e-9 * max(1.0, abs(float(offset)))
