@@ -292,7 +292,7 @@ def run_gpu(args):
             train[key] = {"workload": BT.CONFIGS[cfg][0] + (f" [{mode} step]" if cfg == "c2" else ""),
                           "metric": "train images/sec", "value": imgs / (tms * 1e-3), "unit": "images/s",
                           "batch_per_gpu": batch, "steps": tsteps, "ms_per_step": tms / tsteps,
-                          "scaling": "weak",
+                          "scaling": "weak", **BT.LAST_INFO,
                           "e2e": {"value": imgs / te2e, "unit": "images/s", "h2d_bytes_per_step": th2d,
                                   "d2h_bytes_per_step": 8}}
 

@@ -103,6 +103,9 @@ def _step_fn(cfg, model, mode):
     raise ValueError(cfg)
 
 
+LAST_INFO = {}        # facts about the last gpu_train_rate run that bench.py adds to the JSON line
+
+
 def gpu_train_rate(cfg, qbm, torch, dev, world, rank, barrier, batch, steps, warmup, pg=None, mode="disc"):
     """(images/s device-resident inputs, images/s end to end from host buffers, ms/step) for one config."""
     model = make_model(cfg, qbm, dev, pg)
@@ -135,8 +138,12 @@ def gpu_train_rate(cfg, qbm, torch, dev, world, rank, barrier, batch, steps, war
     e2e_s = time.perf_counter() - t0
     barrier()
     h2d = int(sl(X, 0).nbytes + sl(Y, 0).nbytes)
+    LAST_INFO.clear()
     if hasattr(model, "release_graphs"):
-        model.release_graphs()                  # captured NCCL collectives must not outlive the process group
+        if pg is not None:
+            LAST_INFO["dp_reduce"] = "peer-memory (signal / wait / reduce in rank order / apply in one pass)" if model._peer else "nccl all-reduce + apply"
+            LAST_INFO["peer_error"] = bool(model.peer_error())
+        model.release_graphs()                  # captured NCCL collectives / peer mappings must not outlive the process group
     return ms, e2e_s, h2d
 
 

@@ -198,6 +198,26 @@ int qbm_rbm_cd1_grad(const float *W, const float *Wt, const float *U, const floa
 int qbm_rbm_cd1_grad_dev(const float *W, const float *Wt, const float *U, const float *b_v, const float *b_h, const float *b_c,
                      const float *v0, const int *y0, int B, int V, int H, int C, unsigned long long seed, unsigned int step, const unsigned int *step_dev,
                      float *grad, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Peer-memory form of the all-reduce + apply (ranks of one NVLink node, one process per GPU).  Every rank allocates
+ * qbm_rbm_peer_bytes(V, H, C) with qbm_peer_alloc (plain cudaMalloc, zeroed: two gradient halves | arrival flags | error
+ * word), exports it (64-byte CUDA IPC handle), exchanges the handles by its own means and maps the peers' allocations with
+ * qbm_peer_import.  Per step: the gradient kernels write half `parity` (base + parity * qbm_rbm_grad_count floats), then
+ * qbm_rbm_apply_grad_peer stores `token` into this rank's slot of every rank's flag array, waits until all slots of its own
+ * array have reached `token` (bounded spin: a rank that never arrives sets the error word, see qbm_rbm_peer_error, instead
+ * of hanging the GPU), sums the gradients of all ranks in rank order straight from peer memory and applies them like
+ * qbm_rbm_apply_grad.  parity must alternate and token (+ *tick_dev when given: CUDA-graph replays) must grow by one
+ * every step, on all ranks alike. */
+size_t qbm_rbm_peer_bytes(int V, int H, int C);
+int qbm_peer_alloc(size_t bytes, void **ptr);
+int qbm_peer_free(void *ptr);
+int qbm_peer_export(void *ptr, unsigned char *handle64);
+int qbm_peer_import(const unsigned char *handle64, void **ptr);
+int qbm_peer_close(void *ptr);
+int qbm_rbm_peer_error(const void *own_base, int V, int H, int C, unsigned int *flag_out);
+int qbm_rbm_apply_grad_peer(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, void *const *peer_bases,
+                            int world, int rank, int parity, int V, int H, int C, float scale, float sparse_constant,
+                            float *loss_out, float loss_scale, unsigned int token, const unsigned int *tick_dev, void *stream);
 int qbm_rbm_apply_grad(float *W, float *Wt, float *U, float *b_v, float *b_h, float *b_c, const float *grad, int V, int H,
                        int C, float scale, float sparse_constant, float *loss_out, float loss_scale, void *stream);
 

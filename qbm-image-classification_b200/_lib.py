@@ -53,6 +53,14 @@ SIGNATURES = {
     "qbm_rbm_disc_grad": (_c_i, [_c_p] * 6 + [_c_i] * 4 + [_c_p, _c_p, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_cd1_grad": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [_c_u64, _c_u, _c_p, _c_p, _c_sz, _c_p]),
     "qbm_rbm_cd1_grad_dev": (_c_i, [_c_p] * 8 + [_c_i] * 4 + [_c_u64, _c_u, _c_p, _c_p, _c_p, _c_sz, _c_p]),
+    "qbm_rbm_peer_bytes": (_c_sz, [_c_i, _c_i, _c_i]),
+    "qbm_peer_alloc": (_c_i, [_c_sz, _c_p]),
+    "qbm_peer_free": (_c_i, [_c_p]),
+    "qbm_peer_export": (_c_i, [_c_p, _c_p]),
+    "qbm_peer_import": (_c_i, [_c_p, _c_p]),
+    "qbm_peer_close": (_c_i, [_c_p]),
+    "qbm_rbm_peer_error": (_c_i, [_c_p, _c_i, _c_i, _c_i, _c_p]),
+    "qbm_rbm_apply_grad_peer": (_c_i, [_c_p] * 7 + [_c_i] * 6 + [ctypes.c_float, ctypes.c_float, _c_p, ctypes.c_float, _c_u, _c_p, _c_p]),
     "qbm_rbm_apply_grad": (_c_i, [_c_p] * 7 + [_c_i] * 3 + [ctypes.c_float, ctypes.c_float, _c_p, ctypes.c_float, _c_p]),
     "qbm_disc_param_count": (_c_ll, [_c_i] * 4),
     "qbm_disc_build_qubo": (_c_i, [_c_p, _c_i, _c_i, _c_i, _c_i, _c_p, _c_p, _c_ll, ctypes.c_double, _c_p, _c_p]),

@@ -14,6 +14,7 @@ Reference attributes ``weights [V,H]``, ``visible_bias [V]``, ``hidden_bias [H]`
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 
 import numpy as np
@@ -72,7 +73,7 @@ def gemm_tf32(A: torch.Tensor, B: torch.Tensor, alpha=1.0, beta=0.0, Cin=None, b
 
 class B200ClassificationRBM:
     def __init__(self, num_visible, num_hidden, k, num_classes=2, learning_rate=0.05, sparse_constant=0.00,
-                 use_cuda=True, seed=42, device=None, process_group=None, use_graphs=True):
+                 use_cuda=True, seed=42, device=None, process_group=None, use_graphs=True, peer_reduce=True):
         # same RNG protocol as the reference (:14-15, :26-30): CPU generators, then moved to the device
         np.random.seed(seed)
         torch.manual_seed(seed)
@@ -102,8 +103,12 @@ class B200ClassificationRBM:
         # CD-1 step counter lives on the device)
         self.use_graphs = bool(use_graphs)
         self._graphs = {}
-        self._step_dev = None
-        self._step_dev_val = -1
+        self._ctr = None                   # device counters of the captured steps: [step * world (Philox streams), step (tokens)]
+        self._ctr_val = -1
+        # data-parallel mode: the gradient all-reduce and the update as one pass over NVLink peer memory (csrc/peer.cu)
+        # when every rank of the group can map the others' gradient buffers (one node); else NCCL all-reduce + apply
+        self.peer_reduce = bool(peer_reduce) and os.environ.get("QBM_RBM_PEER_REDUCE", "1") != "0"     # (env: A/B measurements)
+        self._peer = None                  # dict(own=ptr, bases=ctypes array, imported=[ptrs]) once set up; False = not possible
         self.acc_per_epoch_list = []
         self.auc_per_epoch_list = []
 
@@ -221,10 +226,125 @@ class B200ClassificationRBM:
         return ent
 
     def release_graphs(self):
-        """Drop every captured step (they are re-captured on demand).  NCCL cannot tear a communicator down while CUDA graphs
-        that captured its collectives are alive: ``torch.distributed.destroy_process_group`` is wrapped to call this for every
-        live data-parallel model; call it yourself if you destroy the group some other way."""
+        """Drop every captured step (re-captured on demand) and, in data-parallel mode, the peer-mapped gradient buffers (set up
+        again on demand; a COLLECTIVE call there: the ranks meet before the memory goes).  NCCL cannot tear a communicator
+        down while CUDA graphs that captured its collectives are alive either: ``torch.distributed.destroy_process_group`` is
+        wrapped to call this for every live data-parallel model; call it yourself if you destroy the group some other way."""
         self._graphs.clear()
+        self._close_peer()
+
+    # ---- peer-memory gradient buffers (data-parallel mode) -----------------------------------------------------------
+    def _peer_setup(self):
+        """Allocate this rank's IPC-shared gradient allocation, exchange the handles over the process group and map the
+        peers'.  Every rank ends with the same answer (an all-reduce of the outcome), so the ranks never mix the two paths."""
+        if self._peer is not None:
+            return self._peer
+        import torch.distributed as dist
+        L = _lib.load()
+        world, rank = self._world(), self._rank()
+        V, H, C = self.num_visible, self.num_hidden, self.num_classes
+        own, imported, ok = ctypes.c_void_p(), [], 1
+        handles = [None] * world
+        try:
+            if not self.peer_reduce or world > 16:
+                raise RuntimeError("peer reduce switched off")
+            with torch.cuda.device(self.device):
+                _lib.check(L.qbm_peer_alloc(L.qbm_rbm_peer_bytes(V, H, C), ctypes.byref(own)))
+                h = (ctypes.c_ubyte * 64)()
+                _lib.check(L.qbm_peer_export(own, h))
+            mine = bytes(h)
+        except Exception:
+            ok, mine = 0, b""
+        dist.all_gather_object(handles, mine, group=self.pg)
+        bases = (ctypes.c_void_p * world)()
+        if ok and all(len(x) == 64 for x in handles):
+            try:
+                with torch.cuda.device(self.device):
+                    for p in range(world):
+                        if p == rank:
+                            bases[p] = own.value
+                        else:
+                            q = ctypes.c_void_p()
+                            _lib.check(L.qbm_peer_import((ctypes.c_ubyte * 64).from_buffer_copy(handles[p]), ctypes.byref(q)))
+                            imported.append(q)
+                            bases[p] = q.value
+            except Exception:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.pg)         # (also: every rank has mapped before anyone signals)
+        if int(flag.item()) == 1:
+            self._peer = {"own": own, "bases": bases, "imported": imported,
+                          "count": int(L.qbm_rbm_grad_count(V, H, C))}
+            _DP_GRAPH_MODELS.add(self)
+            _hook_destroy_process_group()
+        else:
+            self._peer = {"own": own, "bases": None, "imported": imported, "count": 0}
+            self._close_peer(collective=False)
+            self._peer = False
+        return self._peer
+
+    def _close_peer(self, collective=True):
+        """Unmap the peers' allocations and free this rank's.  A peer may still be reading this rank's last gradient, so the
+        ranks meet first (device synchronised, then a barrier over the group): in data-parallel mode `release_graphs` is a
+        collective call."""
+        pr = self._peer
+        if not pr:
+            return
+        self._peer = None
+        L = _lib.load()
+        try:
+            torch.cuda.synchronize(self.device)
+            if collective and pr.get("bases") is not None:
+                import torch.distributed as dist
+                if dist.is_initialized():
+                    dist.barrier(group=self.pg)
+            with torch.cuda.device(self.device):
+                for q in pr["imported"]:
+                    L.qbm_peer_close(q)
+                if pr["own"].value:
+                    L.qbm_peer_free(pr["own"])
+        except Exception:
+            pass
+
+    def peer_error(self) -> bool:
+        """True when a wait for the peers' gradients ever timed out on this rank (a peer died or fell out of step)."""
+        if not self._peer:
+            return False
+        out = ctypes.c_uint(0)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().qbm_rbm_peer_error(self._peer["own"], self.num_visible, self.num_hidden, self.num_classes,
+                                                      ctypes.byref(out)))
+        return out.value != 0
+
+    def __del__(self):
+        try:
+            self._graphs.clear()
+            self._close_peer(collective=False)
+        except Exception:
+            pass
+
+    def _dp_reduce_apply(self, launch_grads, scale, loss_p, gb, token_host, tick_dev_p):
+        """Data-parallel tail of a step: `launch_grads(grad_ptr)` writes the shard's gradient sums, then either the peer-memory
+        pass (signal, wait, reduce in rank order, apply) or NCCL all-reduce + apply."""
+        L = _lib.load()
+        V, H, C = self.num_visible, self.num_hidden, self.num_classes
+        params = (self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(), self.visible_bias.data_ptr(),
+                  self.hidden_bias.data_ptr(), self.class_bias.data_ptr())
+        pr = self._peer_setup()
+        if pr:
+            parity = self._step & 1
+            launch_grads(pr["own"].value + parity * pr["count"] * 4)
+            self._call(L.qbm_rbm_apply_grad_peer, *params, pr["bases"], self._world(), self._rank(), parity, V, H, C,
+                       float(scale), float(self.sparse_constant), loss_p, float(1.0 / gb), ctypes.c_uint(token_host), tick_dev_p)
+            return
+        import torch.distributed as dist
+        grad = self._grad_buffer()
+        launch_grads(grad.data_ptr())
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
+        self._call(L.qbm_rbm_apply_grad, *params, grad.data_ptr(), V, H, C, float(scale), float(self.sparse_constant), loss_p,
+                   float(1.0 / gb))
 
     def _stage(self, ent, x, y, B):
         V = self.num_visible
@@ -283,7 +403,7 @@ class B200ClassificationRBM:
     def _seed64(self):
         return ctypes.c_uint64(int(self.seed) & (2 ** 64 - 1))
 
-    def _disc_launch(self, B, factor, gb, xp, yp, probs_p, pred_p, loss_p):
+    def _disc_launch(self, B, factor, gb, xp, yp, probs_p, pred_p, loss_p, token_host=0, tick_dev_p=None):
         """All launches of one discriminative step on raw device pointers (run eagerly, or once under graph capture).
         Data-parallel: the gradient sums of this shard into the flat buffer, ONE all-reduce, one fused apply."""
         L = _lib.load()
@@ -295,16 +415,13 @@ class B200ClassificationRBM:
                        float(self.learning_rate), float(factor), float(self.sparse_constant), probs_p, pred_p, loss_p,
                        ws.data_ptr(), ws.numel() * 4)
             return
-        import torch.distributed as dist
-        grad = self._grad_buffer()
-        self._call(L.qbm_rbm_disc_grad, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
-                   self.class_bias.data_ptr(), xp, yp, B, V, H, C, grad.data_ptr(), probs_p, pred_p, ws.data_ptr(), ws.numel() * 4)
-        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
-        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(), V, H, C,
-                   float(factor * self.learning_rate / gb), float(self.sparse_constant), loss_p, float(1.0 / gb))
+        def grads(gp):
+            self._call(L.qbm_rbm_disc_grad, self._Wt.data_ptr(), self._U.data_ptr(), self.hidden_bias.data_ptr(),
+                       self.class_bias.data_ptr(), xp, yp, B, V, H, C, gp, probs_p, pred_p, ws.data_ptr(), ws.numel() * 4)
 
-    def _cd1_launch(self, B, gb, xp, yp, step_host, step_dev_p):
+        self._dp_reduce_apply(grads, factor * self.learning_rate / gb, loss_p, gb, token_host, tick_dev_p)
+
+    def _cd1_launch(self, B, gb, xp, yp, step_host, step_dev_p, token_host=0, tick_dev_p=None):
         """All launches of one CD-1 step; draws are keyed by step_host (+ the device counter when step_dev_p is given)."""
         L = _lib.load()
         ws = self._workspace(B)
@@ -317,14 +434,24 @@ class B200ClassificationRBM:
             self._call(fn, *params, float(self.learning_rate), float(self.sparse_constant), self._seed64(), *step,
                        ws.data_ptr(), ws.numel() * 4)
             return
-        import torch.distributed as dist
-        grad = self._grad_buffer()
         fn = L.qbm_rbm_cd1_grad if step_dev_p is None else L.qbm_rbm_cd1_grad_dev
-        self._call(fn, *params, self._seed64(), *step, grad.data_ptr(), ws.data_ptr(), ws.numel() * 4)
-        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=self.pg)
-        self._call(L.qbm_rbm_apply_grad, self._W.data_ptr(), self._Wt.data_ptr(), self._U.data_ptr(),
-                   self.visible_bias.data_ptr(), self.hidden_bias.data_ptr(), self.class_bias.data_ptr(), grad.data_ptr(), V, H, C,
-                   float(self.learning_rate / gb), float(self.sparse_constant), None, float(1.0 / gb))
+
+        def grads(gp):
+            self._call(fn, *params, self._seed64(), *step, gp, ws.data_ptr(), ws.numel() * 4)
+
+        self._dp_reduce_apply(grads, self.learning_rate / gb, None, gb, token_host, tick_dev_p)
+
+    def _counters(self):
+        """Device counters the captured steps read and advance: [step * world (Philox stream base), step (peer tokens)]."""
+        if self._ctr is None:
+            self._ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
+            self._ctr_inc = torch.tensor([self._world(), 1], dtype=torch.int32, device=self.device)
+        return self._ctr
+
+    def _sync_counters(self):
+        if self._ctr_val != self._step:               # eager steps in between: resynchronise the device counters
+            self._ctr.copy_(torch.tensor([(self._step * self._world()) & 0x3FFFFFFF, self._step & 0x3FFFFFFF], dtype=torch.int32),
+                            non_blocking=True)
 
     def discriminative_training(self, input_data, class_label, factor=1, global_batch=None):
         """:101-146.  Returns (error, predicted, class_probabilities) as CUDA tensors.  With a process group
@@ -335,15 +462,22 @@ class B200ClassificationRBM:
         C, lC = self.num_classes, _ld4(self.num_classes)
         gb = float(global_batch if global_batch is not None else B * self._world())
         if self.use_graphs:
+            ctr = self._counters()
+
             def launch(ent):
                 self._disc_launch(B, factor, gb, ent["x"].data_ptr(), ent["y"].data_ptr(), ent["out"].data_ptr(),
-                                  ent["pred"].data_ptr(), ent["out"].data_ptr() + 4 * B * lC)
+                                  ent["pred"].data_ptr(), ent["out"].data_ptr() + 4 * B * lC, 1, ctr.data_ptr() + 4)
+                ctr.add_(self._ctr_inc)           # part of the graph
 
-            ent = self._graph_entry(("disc", B, float(self.learning_rate), float(factor), float(self.sparse_constant), gb), B, launch)
+            # (data-parallel steps alternate between the two halves of the peer gradient buffer: one capture per parity)
+            ent = self._graph_entry(("disc", B, float(self.learning_rate), float(factor), float(self.sparse_constant), gb,
+                                     self._step & 1 if self.pg is not None else 0), B, launch)
             if ent is not None:
+                self._sync_counters()
                 self._stage(ent, input_data, class_label, B)
                 ent["graph"].replay()
                 self._step += 1
+                self._ctr_val = self._step
                 out = ent["out"].clone()          # the static buffers are overwritten by the next step
                 return out[B * lC], ent["pred"].to(torch.int64), out[:B * lC].view(B, lC)[:, :C]
         x = self._pad_rows(input_data, self.num_visible)
@@ -351,7 +485,8 @@ class B200ClassificationRBM:
         probs = _padded(B, C, self.device)
         pred = torch.empty(B, dtype=torch.int32, device=self.device)
         loss = torch.empty(1, dtype=torch.float32, device=self.device)
-        self._disc_launch(B, factor, gb, x.data_ptr(), y.data_ptr(), probs.data_ptr(), pred.data_ptr(), loss.data_ptr())
+        self._disc_launch(B, factor, gb, x.data_ptr(), y.data_ptr(), probs.data_ptr(), pred.data_ptr(), loss.data_ptr(),
+                          self._step + 1, None)
         self._step += 1
         return loss[0], pred.to(torch.int64), probs[:, :C]
 
@@ -362,25 +497,24 @@ class B200ClassificationRBM:
         world, rank = self._world(), self._rank()
         gb = float(global_batch if global_batch is not None else B * world)
         if self.use_graphs:
-            if self._step_dev is None:
-                self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+            ctr = self._counters()
 
             def launch(ent):
-                self._cd1_launch(B, gb, ent["x"].data_ptr(), ent["y"].data_ptr(), rank, self._step_dev.data_ptr())
-                self._step_dev.add_(world)        # part of the graph: the next replay draws from the next streams
+                self._cd1_launch(B, gb, ent["x"].data_ptr(), ent["y"].data_ptr(), rank, ctr.data_ptr(), 1, ctr.data_ptr() + 4)
+                ctr.add_(self._ctr_inc)           # part of the graph: the next replay draws from the next streams
 
-            ent = self._graph_entry(("cd1", B, float(self.learning_rate), float(self.sparse_constant), gb), B, launch)
+            ent = self._graph_entry(("cd1", B, float(self.learning_rate), float(self.sparse_constant), gb,
+                                     self._step & 1 if self.pg is not None else 0), B, launch)
             if ent is not None:
-                if self._step_dev_val != self._step:          # eager steps in between: resynchronise the device counter
-                    self._step_dev.fill_((self._step * world) & 0x3FFFFFFF)
+                self._sync_counters()
                 self._stage(ent, input_data, class_label, B)
                 ent["graph"].replay()
                 self._step += 1
-                self._step_dev_val = self._step
+                self._ctr_val = self._step
                 return
         v0 = self._pad_rows(input_data, self.num_visible)
         y0 = self._labels(class_label, B)
-        self._cd1_launch(B, gb, v0.data_ptr(), y0.data_ptr(), (self._step * world + rank) & 0x3FFFFFFF, None)
+        self._cd1_launch(B, gb, v0.data_ptr(), y0.data_ptr(), (self._step * world + rank) & 0x3FFFFFFF, None, self._step + 1, None)
         self._step += 1
 
     def predict(self, input_data):
