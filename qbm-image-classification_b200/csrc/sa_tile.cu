@@ -207,6 +207,8 @@ constexpr size_t OFF_ROWMASK = OFF_SPINW + (size_t)MAXSUB * T * 4;
 constexpr size_t OFF_META = OFF_ROWMASK + NREC * 32 * 4;
 constexpr size_t OFF_CTL = OFF_META + NREC * META * 4;
 constexpr size_t OFF_BARS = OFF_CTL + 12 * 4;
+static_assert(31 * T + (NPART - 1) * TS + T <= FXLD, "field-export buffer: last column + its part shift + 16 chains");
+static_assert(OFF_BARS % 8 == 0 && OFF_FX % 16 == 0 && OFF_CBUF % 16 == 0 && OFF_ROWMASK % 4 == 0, "alignment of the carve-up");
 constexpr size_t OFF_RING = (OFF_BARS + (size_t)(2 * NGS + 2 * NREC + 8) * 8 + 127) / 128 * 128;
 
 __host__ __device__ inline size_t tile_smem_bytes(int ld) { return OFF_RING + (size_t)RB * ld * 4; }

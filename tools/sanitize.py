@@ -29,7 +29,9 @@ print("convdeep", c.train_one_iteration(rng.random((3, 10, 10)).astype(np.float3
 r = qbm_b200.B200ClassificationRBM(70, 50, 1, num_classes=4, seed=3, device=dev)
 xb = (rng.random((20, 70)) < 0.3).astype(np.float32)
 yb = rng.integers(0, 4, 20)
-print("rbm", float(r.discriminative_training(xb, yb)[0]))
-r.cd1_training(xb, yb)
+for _ in range(3):                                   # the second step of a shape is captured, the third replayed as a CUDA graph
+    print("rbm", float(r.discriminative_training(xb, yb)[0]))
+for _ in range(3):
+    r.cd1_training(xb, yb)
 torch.cuda.synchronize()
 print("done")
