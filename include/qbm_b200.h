@@ -79,7 +79,7 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned.  With at least
  *                qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads) bytes the sampler may run the two-phase
  *                schedule (n > 896: the chain-tile kernel anneals the hot sweeps, then hands every chain -- fields,
- *                spins, sweep counter -- to the warp-per-chain kernel; identical results, 1.25x (n = 1280) .. 1.65x (n = 2048) faster)
+ *                spins, sweep counter -- to the warp-per-chain kernel; identical results, 1.36x (n = 1280) .. 1.8x (n = 2048) faster)
  *   flags        bit 0: make the warps of a CTA rendezvous at every 128-variable window (A-B measurements; off by
  *                       default because it measured slower)
  *                bit 1: chain g = chain_offset + r for every problem (all problems share one random
@@ -88,7 +88,7 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *                       coupling-row loads; identical trajectories, n > 128 and num_reads >= 2 only)
  *                bit 6: never use the two-phase schedule; bit 7: use it wherever it is supported (n > 896) instead of
  *                       only where it is the measured default (n > QBM_TWO_PHASE_MIN_N); bits 16..23: its hand-over
- *                       threshold in percent of accepted proposals per sweep (0 = default 55)
+ *                       threshold in percent of accepted proposals per sweep (0 = default 50)
  *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed
  *                       by TMA through a shared-memory ring; identical trajectories);
  *                       bits 8..15: its dense/sparse update switch in percent of flipped (chain, variable)
