@@ -36,8 +36,18 @@ def _hook_destroy_process_group():
     orig = dist.destroy_process_group
 
     def destroy_process_group(group=None):
+        # every rank runs this wrapper (SPMD) whatever models it still holds, so the ranks meet HERE, once -- a peer may still
+        # be reading this rank's last gradient -- and the models are then released without further collectives
+        try:
+            if dist.is_initialized() and (group is None or group is dist.group.WORLD):
+                if torch.cuda.is_available():
+                    torch.cuda.synchronize()
+                dist.barrier()
+        except Exception:
+            pass
         for m in list(_DP_GRAPH_MODELS):
-            m.release_graphs()
+            m._graphs.clear()
+            m._close_peer(collective=False)
         return orig(group)
 
     destroy_process_group._qbm_b200_hook = True
