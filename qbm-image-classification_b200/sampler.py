@@ -284,7 +284,30 @@ class B200SASampler:
         samples, _, _ = sample_qubo_batch(Q, int(num_reads), self.num_sweeps, self.seed,
                                           initial_states_generator=self.initial_states_generator,
                                           device=self.device, return_energy=False, process_group=self.process_group)
-        return samples[0].astype(np.float32)
+        return _as_float32(samples[0])
+
+
+def _as_float32(states: np.ndarray) -> np.ndarray:
+    """int8 samples -> the float32 matrix the reference's sampler returns (src/qubo/sampler.py:33).  At the 1e5-read job this
+    is 2e8 values and 819 MB of fresh pages: one core needs ~0.25 s for it (a quarter of the whole call on eight GPUs; measured
+    alternatives -- converting on the device and copying four times the bytes, torch's CPU conversion under torchrun's
+    OMP_NUM_THREADS=1 -- are slower), so large results are converted in row blocks on a few threads (numpy releases the GIL)."""
+    if states.size < (1 << 24):
+        return states.astype(np.float32)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+    threads = max(1, min(8, (os.cpu_count() or 1) // max(1, ranks_here)))
+    out = np.empty(states.shape, dtype=np.float32)
+    rows = states.shape[0]
+    step = (rows + threads - 1) // threads
+
+    def work(i):
+        out[i:i + step] = states[i:i + step]
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(work, range(0, rows, step)))
+    return out
 
 
 def _solve_linear_only(Q: np.ndarray, num_reads: int, seed) -> np.ndarray:

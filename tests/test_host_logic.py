@@ -148,3 +148,13 @@ def test_destroy_process_group_releases_captured_data_parallel_steps():
     finally:
         dist.destroy_process_group()
     assert m.released == 1 and not dist.is_initialized()
+
+
+def test_large_results_are_converted_to_float32_in_row_blocks(qbm):
+    """sample_Q returns float32 like the reference; results of 2^24 values and more are converted on a few threads."""
+    from qbm_b200.sampler import _as_float32
+    rng = np.random.default_rng(3)
+    for shape in ((7, 33), (4099, 4096)):
+        a = rng.integers(0, 2, shape).astype(np.int8)
+        b = _as_float32(a)
+        assert b.dtype == np.float32 and b.shape == a.shape and np.array_equal(b, a.astype(np.float32))
