@@ -217,6 +217,8 @@ class B200ClassificationRBM:
         key = key + tuple(t.data_ptr() for t in (self._W, self._Wt, self._U, self.visible_bias, self.hidden_bias, self.class_bias))
         ent = self._graphs.get(key)
         if ent is None:
+            if len(self._graphs) >= 32:         # shapes / learning rates / re-assigned tensors keep changing: start over
+                self._graphs.clear()
             self._graphs[key] = "warm"
             return None
         if ent == "warm":
