@@ -16,7 +16,8 @@ namespace {
 
 constexpr int MAX_PEERS = 16;
 constexpr int FLAG_WORDS = 64;                 // arrival flags [world] padded; word FLAG_WORDS is the error flag
-constexpr long long SPIN_LIMIT = 6000000000LL; // ~3 s of SM clocks: a rank that never signals must not hang the GPU
+constexpr long long SPIN_LIMIT = 240000000000LL; // ~2 min of SM clocks: a slow rank is waited for (as NCCL would), a dead one
+                                                 // must not hang the GPU for ever
 
 __host__ __device__ inline long long pld4(long long c) { return (c + 3) & ~3LL; }
 inline size_t peer_grad_floats(int V, int H, int C)
@@ -71,16 +72,20 @@ __global__ void __launch_bounds__(256) rbm_apply_peer_kernel(float *__restrict__
 {
     __shared__ float tile[32][33];
     const unsigned int token = token_host + (tick_dev != nullptr ? *tick_dev : 0u);
-    if ((int)threadIdx.x < ps.world) {
+    __shared__ int give_up;
+    if (threadIdx.x == 0) give_up = (ld_acquire_sys(ps.flags[rank] + FLAG_WORDS) != 0u);      // sticky: a broken group stays broken
+    __syncthreads();
+    if ((int)threadIdx.x < ps.world && !give_up) {
         const unsigned int *f = ps.flags[rank] + threadIdx.x;
         const long long t0 = clock64();
         bool ok = false;
         do {
             ok = (int)(ld_acquire_sys(f) - token) >= 0;
         } while (!ok && clock64() - t0 < SPIN_LIMIT);
-        if (!ok) atomicExch(ps.flags[rank] + FLAG_WORDS, 1u);
+        if (!ok) { atomicExch(ps.flags[rank] + FLAG_WORDS, 1u); give_up = 1; }
     }
     __syncthreads();
+    if (give_up) return;                    // no update from a gradient that never arrived; the host raises (qbm_rbm_peer_error)
     const size_t oU = (size_t)V * lH, obv = oU + (size_t)C * lH, obh = obv + pld4(V), obc = obh + pld4(H), oloss = obc + pld4(C);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     if ((int)blockIdx.x < tiles) {

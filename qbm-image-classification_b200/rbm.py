@@ -243,7 +243,11 @@ class B200ClassificationRBM:
         down while CUDA graphs that captured its collectives are alive either: ``torch.distributed.destroy_process_group`` is
         wrapped to call this for every live data-parallel model; call it yourself if you destroy the group some other way."""
         self._graphs.clear()
+        broken = self.peer_error()
         self._close_peer()
+        if broken:
+            raise RuntimeError("a rank of the process group never delivered its gradient (waited ~2 min): the data-parallel "
+                               "updates since then were skipped on this rank")
 
     # ---- peer-memory gradient buffers (data-parallel mode) -----------------------------------------------------------
     def _peer_setup(self):
