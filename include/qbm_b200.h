@@ -78,7 +78,7 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *   counters     nullable uint64[2]: += accepted flips, += proposals
  *   workspace    scratch of at least qbm_sa_workspace_bytes(n, batch_q) bytes, 16-byte aligned.  With at least
  *                qbm_sa_workspace_bytes_two_phase(n, batch_q, num_reads) bytes the sampler may run the two-phase
- *                schedule (n > 896: the chain-tile kernel anneals the hot sweeps, then hands every chain -- fields,
+ *                schedule (by default at n > 896: the chain-tile kernel anneals the hot sweeps, then hands every chain -- fields,
  *                spins, sweep counter -- to the warp-per-chain kernel; identical results, 1.36x (n = 1280) .. 1.8x (n = 2048) faster)
  *   flags        bit 0: make the warps of a CTA rendezvous at every 128-variable window (A-B measurements; off by
  *                       default because it measured slower)
@@ -86,7 +86,7 @@ int qbm_beta_schedule(const double *range, long long batch, int num_betas, float
  *                       stream, as the reference's fixed per-call seed does)
  *                bit 5: use the multi-chain warp kernel (a warp anneals 2-4 chains of one problem and shares their
  *                       coupling-row loads; identical trajectories, n > 128 and num_reads >= 2 only)
- *                bit 6: never use the two-phase schedule; bit 7: use it wherever it is supported (n > 896) instead of
+ *                bit 6: never use the two-phase schedule; bit 7: use it wherever it is supported (n > 256, not 7 windows) instead of
  *                       only where it is the measured default (n > QBM_TWO_PHASE_MIN_N); bits 16..23: its hand-over
  *                       threshold in percent of accepted proposals per sweep (0 = default 50)
  *                bit 4: use the chain-tile kernel (16 chains per CTA share every coupling row, rows streamed

@@ -52,9 +52,9 @@ extern "C" QBM_API size_t qbm_sa_workspace_bytes(int n, long long batch_q)
     return (size_t)batch_q * ((size_t)n + 1) * ld * sizeof(float);
 }
 
-// two-phase schedule (chain-tile kernel for the hot sweeps, then one warp per chain): possible from 8 windows on (both
-// kernels then read the same permuted rows), used by default where it measured faster (profiles/r2_two_phase_sizes.log)
-static inline bool sa_two_phase_supported(int n) { return n > 896 && n <= QBM_SA_MAX_N; }
+// two-phase schedule (chain-tile kernel for the hot sweeps, then one warp per chain): possible where both kernels read the
+// same permuted rows (3..6 and 8..16 windows), used by default where it measured faster (profiles/r2_two_phase_sizes*.log)
+static inline bool sa_two_phase_supported(int n) { return n > 256 && n <= QBM_SA_MAX_N && (n + 127) / 128 != 7; }
 static inline bool sa_two_phase_size(int n) { return n > QBM_TWO_PHASE_MIN_N; }
 
 extern "C" QBM_API size_t qbm_sa_workspace_bytes_two_phase(int n, long long batch_q, long long num_reads)
@@ -130,6 +130,14 @@ extern "C" QBM_API int qbm_sa_sample(const float *J, const float *h, int n, int 
         p.fields = hot.fields; p.sweeps_done = hot.sweeps_done;
         p.init = states_out;
         switch (nw) {
+            // (the code shapes of the plain instantiations: unrolled windows, packed FMAs, shuffled coefficient)
+            // 3..6 windows: opt-in (flag bit 7).  Measured (profiles/r2_two_phase_small_sizes.log): +8..21 % where n fills its
+            // windows and a problem has many reads (n = 384 / 512 / 640 / 768 at 200 reads), -7..9 % at the training shapes
+            // (n = 522: 18 % padding; 100 reads = 6.25 tiles of 16 chains), so the default stays one warp per chain there
+            case 3: return launch_sa<3, 4, 16, 2, true, true, true, true, false, true>(p, st);
+            case 4: return launch_sa<4, 4, 16, 2, true, true, false, true, false, true>(p, st);
+            case 5: return launch_sa<5, 4, 16, 1, true, true, true, true, false, true>(p, st);
+            case 6: return launch_sa<6, 4, 16, 1, true, false, true, true, false, true>(p, st);
             case 8: return launch_sa<8, 4, 16, 1, false, false, true, false, false, true>(p, st);
             case 10: return launch_sa<10, 4, 16, 1, false, false, true, false, false, true>(p, st);
             case 12: return launch_sa<12, 4, 16, 1, false, false, true, false, false, true>(p, st);

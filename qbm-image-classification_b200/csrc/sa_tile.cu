@@ -61,20 +61,30 @@ constexpr int NGS = QBM_TILE_NGS; // ring slots (a power of two)
 constexpr int RB = GR * NGS;      // coupling rows in flight per CTA
 constexpr int NREC = 4;           // record buffers (the scanner runs at most one sub-window ahead of the slowest applier)
 constexpr int FXLD = 32 * T + 32; // floats per field-export buffer: [column][chain], the upper 16 columns shifted by 16
-constexpr int NTHREADS = 384;
-constexpr int WARP_PRODUCER = 8, WARP_BOUNDS = 10;
+// Warp slots of a CTA: AW applier slots (AW = 8: one CTA per SM; AW = 4, problems of at most four 128-variable windows: two
+// CTAs per SM -- there the scanners, whose work per sub-window does not depend on n, bound a CTA, and a second one doubles
+// the SM's rate), then producer, scanner 0, bounds, scanner 1.  setmaxnreg moves registers between the warpgroups:
+//   AW = 8: launched with 168, appliers 208, helpers 88  (2 * 208 + 88 = 504 = 3 * 168)
+//   AW = 4: launched with 128, appliers 160, helpers 96  (160 + 96 = 2 * 128; two CTAs = the whole register file)
+template <int AW> struct Slots {
+    static constexpr int nthreads = (AW + 4) * 32, min_ctas = AW == 8 ? 1 : 2;
+    static constexpr int producer = AW, scanner0 = AW + 1, bounds = AW + 2, scanner1 = AW + 3;
+    static constexpr int regs_applier = AW == 8 ? 208 : 160, regs_helper = AW == 8 ? 88 : 96;
+};
 constexpr int NSCAN = 2;          // scanner warps (warps 9 and 11: one per scheduler that holds no other helper warp)
 constexpr int TS = T / NSCAN;     // chains per scanner warp; lane = chain (TS) x part (32 / TS), a part = TS variables
 constexpr int NPART = 32 / TS;
 static_assert(NSCAN == 1 || NSCAN == 2, "rowmask words are written as 32 / NSCAN-bit halves");
-__device__ __forceinline__ int scanner_of_warp(int warp) { return warp == 9 ? 0 : (NSCAN == 2 && warp == 11 ? 1 : -1); }
+template <int AW> __device__ __forceinline__ int scanner_of_warp(int warp)
+{
+    return warp == Slots<AW>::scanner0 ? 0 : (NSCAN == 2 && warp == Slots<AW>::scanner1 ? 1 : -1);
+}
 // a rowmask word holds, per scanner, TS flip bits then TS old-spin bits: chain t flipped <=> bit flip_bit(t), its old spin
 // is bit flip_bit(t) + TS
 __host__ __device__ constexpr int flip_bit(int t) { return (t / TS) * 2 * TS + (t % TS); }
 // record meta words
 constexpr int META = 8, M_UNION = 0, M_COUNT = 2, M_ROW0 = 4, M_EXIT = 5;
 constexpr uint32_t DENSE_MARK = 0x0fffffffu;
-constexpr int REGS_APPLIER = 208, REGS_HELPER = 88;      // 2 * 208 + 88 = 504 = 3 * 168 (the launch allocation)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
@@ -702,8 +712,8 @@ __device__ __forceinline__ void tile_scanner(const TileSmem &sm, const SaParams 
 }
 
 // NS == 8 (n > 1024): W = windows / 2 applier warps x 8 columns; NS == 4 (n <= 1024): W = windows applier warps x 4 columns.
-template <int NS>
-__global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, const int W, const int ctas_per_problem)
+template <int NS, int AW>
+__global__ void __launch_bounds__(Slots<AW>::nthreads, Slots<AW>::min_ctas) sa_tile_kernel(const SaParams p, const int W, const int ctas_per_problem)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -732,19 +742,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     }
     __syncthreads();
 
-    if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_HELPER));
-        if (warp == WARP_PRODUCER) {
+    if (warp >= AW) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Slots<AW>::regs_helper));
+        if (warp == Slots<AW>::producer) {
             if (lane == 0) tile_producer(sm, Jp, ld);
-        } else if (warp == WARP_BOUNDS) {
+        } else if (warp == Slots<AW>::bounds) {
             tile_bounds(sm, p, betas, chain0, lane);
-        } else if (scanner_of_warp(warp) >= 0) {
+        } else if (scanner_of_warp<AW>(warp) >= 0) {
             tile_sync((W + NSCAN) * 32);                // initial spins written
-            tile_scanner(sm, p, p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj, betas, W, nlive, lane, scanner_of_warp(warp));
+            tile_scanner(sm, p, p.Jnat + (size_t)q * (size_t)n * (size_t)p.ldj, betas, W, nlive, lane, scanner_of_warp<AW>(warp));
         }
         return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_APPLIER));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Slots<AW>::regs_applier));
     if (warp >= W) return;                              // idle warps of the applier warpgroups (W < 8)
 
     // ================================= applier warps =================================
@@ -870,10 +880,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) sa_tile_kernel(const SaParams p, 
     }
 }
 
-template <int NS>
+template <int NS, int AW>
 int launch_tile(const SaParams &p, int W, cudaStream_t st)
 {
-    auto kern = sa_tile_kernel<NS>;
+    auto kern = sa_tile_kernel<NS, AW>;
     const long long cpp = (p.num_reads + T - 1) / T;
     const long long blocks = cpp * p.batch_q;
     if (blocks > 0x7fffffffLL) {
@@ -883,7 +893,7 @@ int launch_tile(const SaParams &p, int W, cudaStream_t st)
     const size_t smem = tile_smem_bytes(p.ld);
     // per launch, not cached: the attribute belongs to the current device, and a process may drive several
     QBM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)blocks, NTHREADS, smem, st>>>(p, W, (int)cpp);
+    kern<<<(unsigned)blocks, Slots<AW>::nthreads, smem, st>>>(p, W, (int)cpp);
     QBM_LAUNCH_OK("sa_tile_kernel");
     return QBM_OK;
 }
@@ -904,8 +914,9 @@ int sa_tile_ld(int n)
 int sa_tile_launch(const SaParams &p, cudaStream_t st)
 {
     const int win = p.ld / 128;
-    if (win <= 8) return launch_tile<4>(p, win, st);                       // n <= 1024: W = win applier warps x 4 columns
-    return launch_tile<8>(p, win / 2, st);                                 // n >  1024: W = win / 2 applier warps x 8 columns
+    if (win <= 4) return launch_tile<4, 4>(p, win, st);                    // n <= 512: the same with four applier slots, two CTAs per SM
+    if (win <= 8) return launch_tile<4, 8>(p, win, st);                    // n <= 1024: W = win applier warps x 4 columns
+    return launch_tile<8, 8>(p, win / 2, st);                              // n >  1024: W = win / 2 applier warps x 8 columns
 }
 
 #ifdef QBM_TILE_PROF

@@ -40,7 +40,9 @@ def test_argument_errors_do_not_need_a_gpu(qbm):
     assert L.qbm_sa_workspace_bytes(24, 3) == 3 * 25 * 128 * 4
     assert L.qbm_sa_workspace_bytes(0, 1) == 0
     # the two-phase workspace adds the hand-over buffers (fields + sweep counters) only where that schedule exists
-    assert L.qbm_sa_workspace_bytes_two_phase(896, 2, 100) == L.qbm_sa_workspace_bytes(896, 2)
+    assert L.qbm_sa_workspace_bytes_two_phase(896, 2, 100) == L.qbm_sa_workspace_bytes(896, 2)          # 7 windows: not supported
+    assert L.qbm_sa_workspace_bytes_two_phase(256, 2, 100) == L.qbm_sa_workspace_bytes(256, 2)
+    assert L.qbm_sa_workspace_bytes_two_phase(512, 2, 100) == L.qbm_sa_workspace_bytes(512, 2) + 200 * 512 * 4 + 800
     assert L.qbm_sa_workspace_bytes_two_phase(1024, 2, 100) == L.qbm_sa_workspace_bytes(1024, 2) + 200 * 1024 * 4 + 800
     assert L.qbm_sa_workspace_bytes_two_phase(2048, 2, 100) == L.qbm_sa_workspace_bytes(2048, 2) + 200 * 2048 * 4 + 800
     assert L.qbm_sa_workspace_bytes_two_phase(1800, 1, 3) == L.qbm_sa_workspace_bytes(1800, 1) + 3 * 2048 * 4 + 16

@@ -220,10 +220,11 @@ def test_sweeps_per_beta_and_single_read(qbm, oracle, cuda, flags):
 
 @pytest.mark.parametrize("n,reads,sweeps,pct", [(2048, 20, 60, 0), (1800, 35, 40, 0), (1930, 17, 50, 97), (2048, 16, 30, 1),
                                                 (2000, 5, 25, 100), (897, 19, 60, 0), (1024, 33, 40, 30), (1290, 17, 40, 0),
-                                                (1536, 20, 50, 0), (1700, 5, 40, 80)])
+                                                (1536, 20, 50, 0), (1700, 5, 40, 80),
+                                                (300, 19, 60, 30), (512, 35, 60, 0), (522, 20, 50, 0), (700, 10, 40, 60)])
 def test_two_phase_schedule_is_the_same_trajectory(qbm, oracle, cuda, n, reads, sweeps, pct):
-    """n > 896: the chain-tile kernel anneals the hot sweeps and hands fields / spins / sweep counters to the warp-per-chain
-    kernel (the default above QBM_TWO_PHASE_MIN_N, flag bit 7 elsewhere).  Same states as with the hand-over switched off
+    """n > 256 (3..6 and 8..16 windows): the chain-tile kernel anneals the hot sweeps and hands fields / spins / sweep counters
+    to the warp-per-chain kernel (the default above QBM_TWO_PHASE_MIN_N, flag bit 7 elsewhere).  Same states as with the hand-over switched off
     (flag bit 6), for any threshold (bits 16..23: 1 % = the tile kernel does everything, 100 % = it hands over after its
     first sweep), partial tiles, two problems with their own schedules, host initial states -- and equal to the replay
     oracle."""
